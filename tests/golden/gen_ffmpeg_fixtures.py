@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ffmpeg_fixtures.npz and crosscheck_report.json -- run in the BUILD container.
+
+    python tests/golden/gen_ffmpeg_fixtures.py
+
+What it pins (SURVEY.md section 8c -- the reference ships no golden vectors, so the pinning the
+reference's own conformance suite does at test time, tests/conformance_test.go:282-332, is done
+here once and committed):
+
+  1. FFmpeg-ENCODED packets for every case below, with sha256 of the SOURCE pcm. Before a case is
+     written the script asserts  oracle(packets) == FFmpeg-decode(packets) == source.
+  2. A cross-check matrix for the test-side encoder (oracle/alac_encoder.c): its packets decode to
+     the source with FFmpeg's decoder AND with the oracle. Summary -> crosscheck_report.json.
+
+The test-suite only reads the .npz (tests/test_oracle_golden.py); it never imports FFmpeg.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import ffmpeg_alac as ff  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+from signals import make_signal  # noqa: E402
+
+# name, bits, channels, rate, frames, signal kind, ffmpeg options
+CASES = [
+    ('s16_stereo_44k', 16, 2, 44100, 9000, 'music', {}),
+    ('s16_mono_8k', 16, 1, 8000, 9000, 'music', {}),
+    ('s16_3ch', 16, 3, 48000, 5000, 'music', {}),
+    ('s16_4ch', 16, 4, 48000, 5000, 'music', {}),
+    ('s16_5ch', 16, 5, 48000, 5000, 'music', {}),
+    ('s16_51', 16, 6, 48000, 9000, 'music', {}),
+    ('s16_61', 16, 7, 48000, 5000, 'music', {}),
+    ('s16_71', 16, 8, 48000, 5000, 'music', {}),
+    ('s24_stereo_96k', 24, 2, 96000, 9000, 'music', {}),
+    ('s24_71_48k', 24, 8, 48000, 9000, 'music', {}),
+    ('s24_mono_192k', 24, 1, 192000, 9000, 'music', {}),
+    ('s16_stereo_order8', 16, 2, 44100, 9000, 'music', {b'min_prediction_order': b'8', b'max_prediction_order': b'8'}),
+    ('s16_stereo_order2', 16, 2, 44100, 5000, 'music', {b'min_prediction_order': b'2', b'max_prediction_order': b'2'}),
+    ('s16_stereo_order7', 16, 2, 44100, 5000, 'music', {b'min_prediction_order': b'7', b'max_prediction_order': b'7'}),
+    ('s16_stereo_order12', 16, 2, 44100, 5000, 'music', {b'min_prediction_order': b'12', b'max_prediction_order': b'12'}),
+    ('s24_stereo_order30', 24, 2, 48000, 5000, 'music', {b'min_prediction_order': b'30', b'max_prediction_order': b'30'}),
+    ('s16_stereo_order1_30', 16, 2, 44100, 9000, 'music', {b'min_prediction_order': b'1', b'max_prediction_order': b'30'}),
+    ('s16_stereo_level0', 16, 2, 44100, 5000, 'music', {b'compression_level': b'0'}),
+    ('s24_stereo_level0', 24, 2, 96000, 5000, 'music', {b'compression_level': b'0'}),
+    ('s16_stereo_silence_lsb', 16, 2, 44100, 20000, 'silence_lsb', {}),
+    ('s24_stereo_silence_lsb', 24, 2, 96000, 20000, 'silence_lsb', {}),
+    ('s16_stereo_white', 16, 2, 44100, 5000, 'white', {}),
+    ('s24_stereo_white', 24, 2, 96000, 5000, 'white', {}),
+    ('s16_stereo_loud', 16, 2, 44100, 9000, 'loud', {}),
+    ('s16_51_silence_lsb', 16, 6, 48000, 12000, 'silence_lsb', {}),
+]
+
+
+def oracle_decode_all(cfg, packets, bits, ch):
+    outs = []
+    for p in packets:
+        st, pcm = ol.decode_packet(cfg, p)
+        assert st == ol.OK, st
+        outs.append(ol.pcm_bytes_to_int(pcm, bits, ch))
+    return np.concatenate(outs)
+
+
+def main():
+    store = {}
+    index = []
+    for name, bits, ch, sr, n, kind, opts in CASES:
+        x = make_signal(kind, ch, n, bits, sr, seed=len(index) + 1)  # [n, ch]
+        cookie, packets = ff.alac_encode(np.ascontiguousarray(x.T), bits, sr, opts)
+        y_ff = ff.alac_decode(cookie, packets, bits, ch, sr).T
+        st, cfg = ol.parse_cookie(cookie)
+        assert st == ol.OK
+        y_or = oracle_decode_all(cfg, packets, bits, ch)
+        assert np.array_equal(y_ff, x), name
+        assert np.array_equal(y_or, x), name
+        pcm = ol.int_to_pcm_bytes(x, bits)
+        store[name + '/cookie'] = np.frombuffer(cookie, dtype=np.uint8)
+        store[name + '/packets'] = np.frombuffer(b''.join(packets), dtype=np.uint8)
+        store[name + '/sizes'] = np.array([len(p) for p in packets], dtype=np.uint32)
+        index.append(dict(name=name, bits=bits, channels=ch, sample_rate=sr, frames=n, kind=kind,
+                          seed=len(index) + 1, pcm_sha256=hashlib.sha256(pcm).hexdigest(),
+                          packets=len(packets), compressed_bytes=sum(len(p) for p in packets)))
+        print(f'{name:28s} packets={len(packets):2d} bytes={sum(len(p) for p in packets):7d} ok')
+    store['index'] = np.frombuffer(json.dumps(index).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, 'ffmpeg_fixtures.npz'), **store)
+
+    # ---- cross-check of the test-side encoder against FFmpeg's decoder ---------------------------
+    report = []
+    seed = 100
+    for bits in (16, 24):
+        for ch in range(1, 9):
+            for kind in ('music', 'silence_lsb', 'white'):
+                for (mn, mx) in ((4, 6), (8, 8), (1, 30), (0, 0), (31, 31)):
+                    seed += 1
+                    sr = 48000
+                    x = make_signal(kind, ch, 6000, bits, sr, seed=seed)
+                    cfg = ol.Config.make(bit_depth=bits, num_channels=ch, sample_rate=sr)
+                    cookie = ol.make_cookie(cfg, wrappers=1)
+                    opts = ol.PacketOpts.make(min_order=mn, max_order=mx)
+                    packets = ol.encode_stream(cfg, x, opts)
+                    y_ff = ff.alac_decode(cookie, packets, bits, ch, sr).T
+                    y_or = oracle_decode_all(cfg, packets, bits, ch)
+                    ok = bool(np.array_equal(y_ff, x) and np.array_equal(y_or, x))
+                    report.append(dict(bits=bits, channels=ch, kind=kind, orders=[mn, mx], ok=ok,
+                                       ratio=round(sum(len(p) for p in packets) / (x.size * bits / 8), 4)))
+                    assert ok, report[-1]
+    # pbFactor / denShift / mixRes sweeps. Kept to parameters where FFmpeg's decoder and the Go reference
+    # agree: FFmpeg reads mixRes as UNSIGNED 8 bits (the reference sign-extends, decoder.go:422) and keeps
+    # int16-wrapping coefficients for every order (the reference keeps int32 for orders 4/5/6/8,
+    # predictor.go:107-110), so negative mixRes and denShift 15 (coefficients pinned at the int16 limit)
+    # legitimately differ there; those shapes are pinned by the restatement only.
+    for (pbf, den, mb_, mr) in ((4, 9, 0, 0), (2, 7, 2, 1), (7, 12, 2, 3), (1, 4, 5, 3), (4, 9, 31, 1), (3, 11, 8, 100)):
+        seed += 1
+        x = make_signal('music', 2, 6000, 16, 44100, seed=seed)
+        cfg = ol.Config.make(bit_depth=16, num_channels=2, sample_rate=44100)
+        cookie = ol.make_cookie(cfg, wrappers=1)
+        opts = ol.PacketOpts.make(pb_factor=pbf, den_shift=den, mix_bits=mb_, mix_res=mr)
+        packets = ol.encode_stream(cfg, x, opts)
+        y_ff = ff.alac_decode(cookie, packets, 16, 2, 44100).T
+        y_or = oracle_decode_all(cfg, packets, 16, 2)
+        ok = bool(np.array_equal(y_ff, x) and np.array_equal(y_or, x))
+        report.append(dict(bits=16, channels=2, kind='music', pb_factor=pbf, den_shift=den, mix=[mb_, mr], ok=ok))
+        assert ok, report[-1]
+    with open(os.path.join(HERE, 'crosscheck_report.json'), 'w') as f:
+        json.dump(dict(what='test-side encoder -> FFmpeg decoder == oracle == source', cases=len(report),
+                       all_ok=all(r['ok'] for r in report), results=report), f, indent=0)
+    print('crosscheck cases', len(report), 'all ok', all(r['ok'] for r in report))
+
+
+if __name__ == '__main__':
+    main()
