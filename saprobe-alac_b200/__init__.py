@@ -225,7 +225,7 @@ class PacketDecoder:
         n = len(sizes)
         out_stride = out_stride or (self.frame_bytes + 3) // 4 * 4
         if out is None:
-            out = np.empty((n, out_stride), dtype=np.uint8)
+            out = np.zeros((n, out_stride), dtype=np.uint8)
         nb = np.zeros(n, dtype=np.uint32)
         st = np.zeros(n, dtype=np.int32)
         packed = np.ascontiguousarray(packed, dtype=np.uint8)
