@@ -189,6 +189,27 @@ def pack_packets(packets, align=16):
     return packed, offsets, sizes
 
 
+def shard_ranges(weights, world: int):
+    """Contiguous [lo, hi) ranges, one per rank, balanced by `weights` (compressed bytes per packet or per
+    track). Packets/tracks are independent (decoder.go:79-87), so multi-GPU decode is a plain partition:
+    no collective on the data path, output order = input order."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = len(w)
+    world = max(1, int(world))
+    if n == 0:
+        return [(0, 0)] * world
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        k = int(np.searchsorted(cum, target, side='left'))
+        k = max(bounds[-1], min(k, n))
+        bounds.append(k)
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
 # ---- decoder.go ---------------------------------------------------------------------------------------
 class PacketDecoder:
     """PacketDecoder, decoder.go:79-128, on one CUDA device."""
