@@ -160,7 +160,7 @@ int32_t launch(alacb200_decoder *dec, Work &work, const uint8_t *d_packed, const
         CU(cudaEventCreate(&pe.e2));
         CU(cudaEventRecord(pe.e0, stream));
     }
-    alac_decode_kernel<<<groups, 32, 0, stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
+    alac_decode_kernel<<<groups, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
                                                   (PacketDesc *)work.descs.p, d_out_bytes, d_status);
     CU(cudaGetLastError());
     if (dec->profiling) CU(cudaEventRecord(pe.e1, stream));
@@ -272,6 +272,11 @@ int32_t alacb200_create(const alacb200_config *cfg, int device, alacb200_decoder
     cudaError_t e = cudaFuncSetAttribute(alac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)emit_smem_bytes(dec->dev_cfg));
     if (!cuda_ok(e, "cudaFuncSetAttribute(alac_emit_kernel)")) {
+        delete dec;
+        return ALACB200_E_CUDA;
+    }
+    e = cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    if (!cuda_ok(e, "cudaFuncSetAttribute(alac_decode_kernel)")) {
         delete dec;
         return ALACB200_E_CUDA;
     }

@@ -2,14 +2,17 @@
 //
 // Two kernels, both parallel ACROSS packets (packets are independent, decoder.go:79-87):
 //
-//   alac_decode_kernel  stage 1+2. One thread per packet, one warp = 32 packets. Walks the element
-//                       grammar of decodePacketInto (decoder.go:133-207), and per channel runs the
-//                       adaptive Golomb-Rice decoder (DynDecomp, golomb.go:148-253) FUSED with the
-//                       sign-LMS predictor (UnpcBlock, predictor.go:45-684): residuals never leave
-//                       registers. Decoded channel samples are parked as int32 in a lane-interleaved
-//                       scratch ([group][slot][sample][32 lanes]) so every warp store is one 128-byte line.
-//                       Compressed bytes are pulled with 128-bit loads into a per-lane register
-//                       bit reservoir (2 x uint4 deep prefetch).
+//   alac_decode_kernel  stage 1+2. One CTA = 32 packets, three role warps with lane = packet: an ENTROPY
+//                       warp walks the element grammar of decodePacketInto (decoder.go:133-207) and
+//                       the adaptive Golomb-Rice stream (DynDecomp, golomb.go:148-253) and hands
+//                       residuals through a shared-memory ring (mbarrier full/empty pairs) to two
+//                       PREDICTOR warps running the sign-LMS filter (UnpcBlock, predictor.go:45-684),
+//                       one for the mono/U stream and one for the V stream of every element, so the
+//                       serial entropy chain of a packet overlaps both predictor chains. Compressed
+//                       bytes are staged into shared memory with 128-bit cp.async (zero-fill past the
+//                       packet end) one period ahead of their use. Decoded channel samples are parked
+//                       as int32 in a lane-interleaved scratch ([group][slot][sample][32 lanes]) so
+//                       every warp store is one 128-byte line.
 //   alac_emit_kernel    stage 3. Fully data-parallel un-mix + shift-merge + interleaved little-endian
 //                       PCM emit (WriteStereo*/WriteMono*, matrix.go:30-301) through a shared-memory
 //                       transpose so global stores are coalesced / 128-bit.
@@ -127,68 +130,127 @@ __device__ __forceinline__ uint32_t cur_read_one(const Packet &pk, Cursor &c) { 
     return v;
 }
 
-// ---- register bit reservoir for the hot loops ---------------------------------------------------
-// 64-bit window (hi:lo, big-endian order) + one uint4 of queued words + one uint4 in flight.
-struct BitRes {
-    const uint4 *base;  // 16-byte aligned address at or below the packet start
-    uint32_t end_rel;   // packet end, in bytes relative to base
-    uint32_t nchunk;    // next chunk index to prefetch
-    uint4 cur, pf;
-    uint32_t widx;  // next word of cur
-    uint32_t hi, lo;
-    uint32_t sh;  // bits of hi already consumed (0..31)
+// ---- mbarrier (shared-memory producer/consumer barriers between the role warps) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
 
-    __device__ __forceinline__ uint4 load_chunk(uint32_t c) const {
-        uint32_t b0 = c << 4;
-        if (b0 >= end_rel) return make_uint4(0, 0, 0, 0);
-        uint4 v = __ldg(base + c);
-        if (b0 + 16u > end_rel) {  // bytes past the packet end read as zero (the reference's 4-byte pad)
-            uint32_t keep = end_rel - b0;  // 1..15 bytes valid
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t lo_b = (uint32_t)i * 4u;
-                if (keep <= lo_b) w[i] = 0;
-                else if (keep < lo_b + 4u) w[i] &= (1u << ((keep - lo_b) * 8u)) - 1u;
-            }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        return v;
+// ---- geometry of one decode CTA ---------------------------------------------------------------------
+// 3 warps, 32 packets: one ENTROPY warp (lane = packet) walks the grammar and the Golomb stream and hands
+// residuals, 32 samples at a time, through a shared-memory ring to two PREDICTOR warps (lane = packet):
+// consumer 0 takes the mono / U stream of every element, consumer 1 the V stream. The serial entropy chain
+// of a packet (U then V, golomb.go) therefore overlaps with both predictor chains.
+constexpr int DEC_THREADS = 96;
+constexpr int RING_SLOTS = 4;    // ring depth per consumer
+constexpr int CHUNK = 32;        // samples per ring slot
+constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged per lane (512 B window)
+
+struct DecShared {
+    int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (32 KB)
+    uint32_t job[2][RING_SLOTS][4][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax
+    uint4 fifo[FIFO_CHUNKS][32];             // compressed bytes staged by cp.async, [chunk][lane]       (16 KB)
+    uint64_t full_bar[2][RING_SLOTS];
+    uint64_t empty_bar[2][RING_SLOTS];
+};
+
+// job meta word
+enum : uint32_t { JOB_INACTIVE = 0, JOB_REG = 1, JOB_GENERIC = 2, JOB_EXIT = 3 };
+__device__ __forceinline__ uint32_t job_meta(uint32_t kind, uint32_t order, uint32_t den, uint32_t mode, uint32_t chan_bits,
+                                             uint32_t slot) {
+    return kind | (order << 2) | (den << 7) | ((mode != 0 ? 1u : 0u) << 11) | (chan_bits << 12) | (slot << 18);
+}
+
+// ---- bit reader of the entropy warp -----------------------------------------------------------------
+// The compressed packet is staged into shared memory with 128-bit cp.async (zero-filled past the packet
+// end = the reference's zero padding, bitbuffer.go:36-51) one ring-chunk period ahead of its use; the
+// hot loop then needs one LDS per sample, issued at the top of the iteration, and a branch-free refill.
+struct BitReader {
+    const uint8_t *gbase;  // 16-byte aligned global address at or below the packet start
+    uint32_t end_rel;      // packet end, bytes from gbase
+    uint32_t fifo;         // shared address of fifo[0][lane]
+    uint32_t req;          // next 16-byte chunk to request
+    uint32_t q;            // word index (from gbase) held in hi; lo holds q+1
+    uint32_t hi, lo, nxt;  // big-endian-converted words
+    uint32_t sh;           // bits of hi already consumed (0..31)
+
+    __device__ __forceinline__ void request(uint32_t c) {
+        const uint32_t b0 = c << 4;
+        uint32_t nbytes = b0 >= end_rel ? 0u : min(16u, end_rel - b0);
+        const uint8_t *src = gbase + (nbytes ? b0 : 0u);
+        const uint32_t dst = fifo + ((c & (FIFO_CHUNKS - 1)) * 32u) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
     }
-    __device__ __forceinline__ uint32_t pop() {
-        uint32_t w = widx == 0 ? cur.x : widx == 1 ? cur.y : widx == 2 ? cur.z : cur.w;
-        widx++;
-        if (widx == 4) {
-            cur = pf;
-            pf = load_chunk(nchunk++);
-            widx = 0;
-        }
-        return __byte_perm(w, 0, 0x0123);
+    __device__ __forceinline__ static void wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+    __device__ __forceinline__ uint32_t load(uint32_t widx) const {
+        const uint32_t a = fifo + (((widx >> 2) & (FIFO_CHUNKS - 1)) * 32u) * 16u + (widx & 3u) * 4u;
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return __byte_perm(v, 0, 0x0123);
     }
-    // position the window at absolute packet bit position bp
-    __device__ __forceinline__ void init(const Packet &pk, uint32_t bp) {
-        uintptr_t a = (uintptr_t)pk.p;
-        uint32_t mis = (uint32_t)(a & 15u);
-        base = (const uint4 *)(a - mis);
+    // called once per ring chunk: land what was requested a period ago, request up to a full window ahead
+    __device__ __forceinline__ void top_up() {
+        wait_all();
+        const uint32_t lim = ((q + 2u) >> 2) + FIFO_CHUNKS;
+        while (req < lim) request(req++);
+    }
+    __device__ __forceinline__ void init(const Packet &pk, uint32_t bp, uint32_t fifo_addr) {
+        const uintptr_t a = (uintptr_t)pk.p;
+        const uint32_t mis = (uint32_t)(a & 15u);
+        gbase = pk.p - mis;
         end_rel = mis + pk.size;
-        uint32_t abp = bp + mis * 8u;
-        uint32_t c = abp >> 7;
-        cur = load_chunk(c);
-        pf = load_chunk(c + 1);
-        nchunk = c + 2;
-        widx = (abp >> 5) & 3u;
-        hi = pop();
-        lo = pop();
+        fifo = fifo_addr;
+        const uint32_t abp = bp + mis * 8u;
+        q = abp >> 5;
         sh = abp & 31u;
+        wait_all();  // nothing of a previous element may still be landing in the window
+        req = q >> 2;
+        const uint32_t lim = req + FIFO_CHUNKS;
+        while (req < lim) request(req++);
+        wait_all();
+        hi = load(q);
+        lo = load(q + 1u);
+        nxt = load(q + 2u);
     }
+    // top of every sample iteration: (re)load the word after lo; its latency hides behind the decode
+    __device__ __forceinline__ void begin_sample() { nxt = load(q + 2u); }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, sh); }
-    __device__ __forceinline__ void consume(uint32_t nb) {
+    // first consume of an iteration: branch-free, at most one refill from the preloaded nxt
+    __device__ __forceinline__ void consume_hot(uint32_t nb) {
         sh += nb;
+        const bool need = sh >= 32u;
+        hi = need ? lo : hi;
+        lo = need ? nxt : lo;
+        q += need ? 1u : 0u;
+        sh -= need ? 32u : 0u;
+        if (sh >= 32u) consume_more();
+    }
+    // any further consume: reloads as it goes
+    __device__ __forceinline__ void consume_more() {
         while (sh >= 32u) {
             hi = lo;
-            lo = pop();
+            lo = load(q + 2u);
+            q += 1u;
             sh -= 32u;
         }
+    }
+    __device__ __forceinline__ void consume_slow(uint32_t nb) {
+        sh += nb;
+        consume_more();
     }
 };
 
@@ -201,7 +263,7 @@ struct Entropy {
 };
 
 // Decodes the residual of sample index i (0-based) of n. Returns false and sets st on error.
-__device__ __forceinline__ bool entropy_next(const Packet &pk, BitRes &br, uint32_t &bp, Entropy &e, uint32_t i,
+__device__ __forceinline__ bool entropy_next(const Packet &pk, BitReader &br, uint32_t &bp, Entropy &e, uint32_t i,
                                              uint32_t n, int32_t &res, int32_t &st) {
     if (e.zrun > 0) {  // inside a zero run (clear(predCoefs[count:end]), golomb.go:237)
         e.zrun--;
@@ -216,15 +278,15 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitRes &br, uint3
     uint32_t k = 31u - (uint32_t)__clz((int32_t)(m + 3u));
     k = min(k, e.kb);
     m = shl_go(1u, k) - 1u;
-    uint32_t w = br.window();
+    const uint32_t w = br.window();
     uint32_t r = (uint32_t)__clz((int32_t)~w);
     if (r >= 9u) {
         // getStreamBits(input, bitPos+9, maxSize), golomb.go:86-108
-        uint32_t bo = bp + 9u;
-        uint32_t byte_off = bo >> 3;
+        const uint32_t bo = bp + 9u;
+        const uint32_t byte_off = bo >> 3;
         if (byte_off > pk.size) { st = ST_REF_PANIC; return false; }
-        uint32_t load1 = pk_be32(pk, byte_off);
-        uint32_t nb = e.max_size;
+        const uint32_t load1 = pk_be32(pk, byte_off);
+        const uint32_t nb = e.max_size;
         if (nb + (bo & 7u) > 32u) {
             if (byte_off >= pk.size) { st = ST_REF_PANIC; return false; }
             uint32_t v = load1 << (bo & 7u);
@@ -238,25 +300,20 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitRes &br, uint3
             r = v;
         }
         bp += 9u + nb;
-        br.consume(9u + nb);
+        br.consume_slow(9u + nb);
     } else {
-        uint32_t nb = r + 1u;
-        if (k != 1u) {
-            uint32_t s = w << nb;
-            uint32_t v = shr_go(s, 32u - k);
-            if (v >= 2u) {
-                r = r * m + v - 1u;
-                nb += k;
-            } else {
-                r = r * m;
-                nb += k - 1u;
-            }
-        }
+        // prefix r, then a k-bit suffix v; v < 2 means "no suffix value" and gives one bit back. k == 1 and
+        // k == 0 fall out of the same formula (golomb.go:188-201): m = 1 / 0 and v < 2 always.
+        const uint32_t s = w << (r + 1u);
+        const uint32_t v = shr_go(s, 32u - k);
+        const bool big = v >= 2u;
+        const uint32_t nb = r + k + (big ? 1u : 0u);
+        r = r * m + (big ? v - 1u : 0u);
         bp += nb;
-        br.consume(nb);
+        br.consume_hot(nb);
     }
-    uint32_t nd = r + e.zmode;
-    int32_t mag = (int32_t)((nd + 1u) >> 1);
+    const uint32_t nd = r + e.zmode;
+    const int32_t mag = (int32_t)((nd + 1u) >> 1);
     res = (nd & 1u) ? -mag : mag;
     e.mean = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
     if (r > 0xffffu) e.mean = 0xffffu;
@@ -266,18 +323,18 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitRes &br, uint3
         e.zmode = 1;
         int32_t k32 = __clz((int32_t)e.mean) - 24 + (int32_t)((e.mean + 16u) >> 6);
         if (k32 < 0) k32 = 0;
-        uint32_t mz = (shl_go(1u, (uint32_t)k32) - 1u) & e.wb;
+        const uint32_t mz = (shl_go(1u, (uint32_t)k32) - 1u) & e.wb;
         if ((bp >> 3) > pk.size) { st = ST_REF_PANIC; return false; }
-        uint32_t w2 = br.window();
-        uint32_t pre = (uint32_t)__clz((int32_t)~w2);
+        const uint32_t w2 = br.window();
+        const uint32_t pre = (uint32_t)__clz((int32_t)~w2);
         uint32_t run, nb;
         if (pre >= 9u) {
             run = (w2 << 9) >> 16;
             nb = 25u;
         } else {
             nb = pre + 1u;
-            uint32_t s = shl_go(w2, nb);
-            uint32_t val = shr_go(s, 32u - (uint32_t)k32);
+            const uint32_t s = shl_go(w2, nb);
+            const uint32_t val = shr_go(s, 32u - (uint32_t)k32);
             nb += (uint32_t)k32;
             if (val < 2u) {
                 run = pre * mz;
@@ -287,7 +344,7 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitRes &br, uint3
             }
         }
         bp += nb;
-        br.consume(nb);
+        br.consume_slow(nb);
         if (i + 1u + run > n) {  // golomb.go:232-234
             st = ST_SAMPLE_OVERRUN;
             return false;
@@ -299,215 +356,20 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitRes &br, uint3
     return true;
 }
 
-// Per-channel header, decoder.go:275-286.
-struct ChanHdr {
-    uint32_t mode, den_shift, pb_factor, num;
-    int16_t coefs[32];
-};
-__device__ __forceinline__ void read_chan_hdr(const Packet &pk, Cursor &c, ChanHdr &h) {
-    uint32_t hb = cur_read(pk, c, 8);
-    h.mode = hb >> 4;
-    h.den_shift = hb & 0xfu;
-    hb = cur_read(pk, c, 8);
-    h.pb_factor = hb >> 5;
-    h.num = hb & 0x1fu;
-#pragma unroll 1
-    for (uint32_t i = 0; i < 32; i++) h.coefs[i] = (i < h.num) ? (int16_t)cur_read(pk, c, 16) : (int16_t)0;
-}
-
-// Order-31 pre-pass state (mode != 0: UnpcBlock(pred, pred, n, nil, 31, chanBits, 0), decoder.go:306-308)
-struct Delta {
-    bool on;
-    int32_t prev;
-};
-__device__ __forceinline__ int32_t delta_step(Delta &d, int32_t r, uint32_t i, uint32_t cs) {
-    if (!d.on) return r;
-    d.prev = (i == 0) ? r : sext_go(r + d.prev, cs);
-    return d.prev;
-}
-
-// ---- fused entropy + predictor loops ---------------------------------------------------------------
-// T-tap register predictor for orders with int32 coefficient semantics (unpcBlock4/5/6/8,
-// predictor.go:99-618). T=6 serves orders 4,5,6 (taps >= order are masked); T=8 serves order 8.
-template <int T>
-__device__ __forceinline__ int32_t channel_fixed(const Packet &pk, BitRes &br, uint32_t &bp, Entropy &e,
-                                                 const ChanHdr &hd, uint32_t n, uint32_t chan_bits,
-                                                 int32_t *__restrict__ dst) {
-    const uint32_t cs = 32u - chan_bits;
-    const uint32_t den = hd.den_shift;
-    const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
-    const int32_t order = (T == 8) ? 8 : (int32_t)hd.num;
-    int32_t c[T], h[T + 1], wgt[T];
-    bool in_tap[T];
-#pragma unroll
-    for (int j = 0; j < T; j++) {
-        c[j] = (j < order) ? (int32_t)hd.coefs[j] : 0;
-        wgt[j] = (j < order) ? order - j : 0;
-        in_tap[j] = j < order;
-    }
-#pragma unroll
-    for (int j = 0; j <= T; j++) h[j] = 0;
-    Delta dl{hd.mode != 0, 0};
-    int32_t st = ST_OK;
-#pragma unroll 1
-    for (uint32_t i = 0; i < n; i++) {
-        int32_t r;
-        if (!entropy_next(pk, br, bp, e, i, n, r, st)) return st;
-        r = delta_step(dl, r, i, cs);
-        int32_t top;
-        if (T == 8) top = h[8];
-        else top = (order == 4) ? h[4] : (order == 5) ? h[5] : h[6];
-        int32_t d[T];
-        int32_t sum = den_half;
-#pragma unroll
-        for (int j = 0; j < T; j++) {
-            d[j] = top - h[j];
-            sum -= c[j] * d[j];
-        }
-        const int32_t fir = sext_go(r + top + (sum >> den), cs);
-        const int32_t warm = (i == 0) ? r : sext_go(r + h[0], cs);
-        const bool is_fir = (int32_t)i > order;
-        const int32_t x = is_fir ? fir : warm;
-        // sign-LMS adaptation on the residual's sign
-        bool alive = is_fir && (r != 0);
-        const int32_t smask = r >> 31;      // 0 / -1
-        const int32_t thr = 1 + smask;      // continue while (D ^ smask) >= thr  <=>  D > 0 (r>0) / D < 0 (r<0)
-        int32_t D = r;
-#pragma unroll
-        for (int j = T - 1; j >= 0; j--) {
-            const int32_t sg = sign_of(d[j]);
-            const int32_t sgn = (sg ^ smask) - smask;  // sg for r>0, -sg for r<0
-            const bool act = alive && in_tap[j];
-            if (act) c[j] -= sgn;
-            if (j > 0) {
-                const int32_t term = (sgn * d[j]) >> den;
-                D -= wgt[j] * term;  // wgt == 0 for masked taps
-                alive = alive && (!in_tap[j] || ((D ^ smask) >= thr));
-            }
-        }
-#pragma unroll
-        for (int j = T; j > 0; j--) h[j] = h[j - 1];
-        h[0] = x;
-        dst[(size_t)i * 32u] = x;
-    }
-    return ST_OK;
-}
-
-// Orders 0 (copy) and 31 (first-order delta), predictor.go:55-72.
-__device__ __forceinline__ int32_t channel_simple(const Packet &pk, BitRes &br, uint32_t &bp, Entropy &e,
-                                                  const ChanHdr &hd, uint32_t n, uint32_t chan_bits,
-                                                  int32_t *__restrict__ dst) {
-    const uint32_t cs = 32u - chan_bits;
-    Delta dl{hd.mode != 0, 0};
-    const bool acc = hd.num == 31;
-    int32_t prev = 0, st = ST_OK;
-#pragma unroll 1
-    for (uint32_t i = 0; i < n; i++) {
-        int32_t r;
-        if (!entropy_next(pk, br, bp, e, i, n, r, st)) return st;
-        r = delta_step(dl, r, i, cs);
-        int32_t x = r;
-        if (acc && i > 0) x = sext_go(r + prev, cs);
-        prev = x;
-        dst[(size_t)i * 32u] = x;
-    }
-    return ST_OK;
-}
-
-// Every other order: unpcBlockGeneral, predictor.go:623-684 (int16 coefficients, wrap on update).
-__device__ __noinline__ int32_t channel_general(const Packet &pk, BitRes &br, uint32_t &bp, Entropy &e, ChanHdr &hd,
-                                                uint32_t n, uint32_t chan_bits, int32_t *__restrict__ dst) {
-    const uint32_t cs = 32u - chan_bits;
-    const uint32_t den = hd.den_shift;
-    const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
-    const int32_t order = (int32_t)hd.num;
-    int32_t hist[32];  // ring: out[i] at hist[i & 31]
-    Delta dl{hd.mode != 0, 0};
-    int32_t st = ST_OK;
-#pragma unroll 1
-    for (uint32_t i = 0; i < n; i++) {
-        int32_t r;
-        if (!entropy_next(pk, br, bp, e, i, n, r, st)) return st;
-        r = delta_step(dl, r, i, cs);
-        int32_t x;
-        if (i == 0) x = r;
-        else if ((int32_t)i <= order) x = sext_go(r + hist[(i - 1) & 31u], cs);
-        else {
-            const int32_t top = hist[(i - (uint32_t)order - 1u) & 31u];
-            int32_t sum1 = 0;
-#pragma unroll 1
-            for (int32_t k = 0; k < order; k++) sum1 += (int32_t)hd.coefs[k] * (hist[(i - 1u - (uint32_t)k) & 31u] - top);
-            x = sext_go(r + top + ((sum1 + den_half) >> den), cs);
-            int32_t del0 = r;
-            if (r > 0) {
-#pragma unroll 1
-                for (int32_t k = order - 1; k >= 0; k--) {
-                    int32_t dd = top - hist[(i - 1u - (uint32_t)k) & 31u];
-                    int32_t sgn = sign_of(dd);
-                    hd.coefs[k] = (int16_t)(hd.coefs[k] - (int16_t)sgn);
-                    del0 -= (order - k) * ((sgn * dd) >> den);
-                    if (del0 <= 0) break;
-                }
-            } else if (r < 0) {
-#pragma unroll 1
-                for (int32_t k = order - 1; k >= 0; k--) {
-                    int32_t dd = top - hist[(i - 1u - (uint32_t)k) & 31u];
-                    int32_t sgn = sign_of(dd);
-                    hd.coefs[k] = (int16_t)(hd.coefs[k] + (int16_t)sgn);
-                    del0 -= (order - k) * ((-sgn * dd) >> den);
-                    if (del0 >= 0) break;
-                }
-            }
-        }
-        hist[i & 31u] = x;
-        dst[(size_t)i * 32u] = x;
-    }
-    return ST_OK;
-}
-
-// One compressed channel: SetAGParams + DynDecomp + UnpcBlock (decoder.go:296-312).
-__device__ __forceinline__ int32_t decode_channel(const Packet &pk, const DevConfig &cfg, BitRes &br, uint32_t &bp,
-                                                  ChanHdr &hd, uint32_t n, uint32_t chan_bits,
-                                                  int32_t *__restrict__ dst) {
-    // DynDecomp entry: input := Buf[Pos:] (golomb.go:149) and the first read32bit when Pos > Size
-    const uint32_t pos = bp >> 3;
-    if (pos > pk.size + 4u) return ST_REF_PANIC;
-    if (n > 0 && pos > pk.size) return ST_REF_PANIC;
-    Entropy e;
-    e.mean = cfg.mb;
-    e.zmode = 0;
-    e.zrun = 0;
-    e.pb = (cfg.pb * hd.pb_factor) / 4u;
-    e.kb = cfg.kb;
-    e.wb = shl_go(1u, cfg.kb) - 1u;
-    e.max_size = chan_bits;
-    e.size8 = pk.size * 8u;
-    const uint32_t ord = hd.num;
-    int32_t st;
-    if (ord >= 4 && ord <= 6) st = channel_fixed<6>(pk, br, bp, e, hd, n, chan_bits, dst);
-    else if (ord == 8) st = channel_fixed<8>(pk, br, bp, e, hd, n, chan_bits, dst);
-    else if (ord == 0 || ord == 31) st = channel_simple(pk, br, bp, e, hd, n, chan_bits, dst);
-    else st = channel_general(pk, br, bp, e, hd, n, chan_bits, dst);
-    // the warm-up indexes [1..numActive] of frame_length-long slices (predictor.go:76-79); it runs after
-    // DynDecomp, so an entropy error wins
-    if (st == ST_OK && ord != 0 && ord != 31 && ord >= cfg.frame_length) st = ST_REF_PANIC;
-    return st;
-}
-
 // decodeSCEEscape / decodeCPEEscape, decoder.go:326-345, :504-535
-__device__ __forceinline__ int32_t escape_sample(BitRes &br, uint32_t chan_bits) {
+__device__ __forceinline__ int32_t escape_sample(BitReader &br, uint32_t chan_bits) {
     const uint32_t shift = 32u - chan_bits;
     if (chan_bits <= 16u) {
-        int32_t val = (int32_t)shr_go(br.window(), 32u - chan_bits);
-        br.consume(chan_bits);
+        const int32_t val = (int32_t)shr_go(br.window(), 32u - chan_bits);
+        br.consume_slow(chan_bits);
         return sext_go(val, shift);
     }
     const uint32_t extra = chan_bits - 16u;
     int32_t val = (int32_t)(br.window() >> 16);
-    br.consume(16u);
+    br.consume_slow(16u);
     val = sar_go((int32_t)((uint32_t)val << 16), shift);
-    int32_t lo = (int32_t)shr_go(br.window(), 32u - extra);
-    br.consume(extra);
+    const int32_t lo = (int32_t)shr_go(br.window(), 32u - extra);
+    br.consume_slow(extra);
     return val | lo;
 }
 
@@ -515,155 +377,555 @@ __constant__ int8_t k_layout[8][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 
                                       {2, 0, 1, 3, 0, 0, 0, 0}, {2, 0, 1, 3, 4, 0, 0, 0}, {2, 0, 1, 4, 5, 3, 0, 0},
                                       {2, 0, 1, 4, 5, 6, 3, 0}, {2, 6, 7, 0, 1, 4, 5, 3}};
 
-// decodeSCE / decodeCPE (decoder.go:210-265, :348-414) minus the writer, which becomes an OpDesc.
-__device__ __forceinline__ int32_t decode_element(const Packet &pk, const DevConfig &cfg, Cursor &cur, bool stereo,
-                                                  uint32_t chan_idx, uint32_t &ns, int32_t *__restrict__ scratch_lane,
-                                                  PacketDesc *__restrict__ desc, uint32_t &nops) {
-    (void)cur_read_small(pk, cur, 4);
-    uint32_t unused = cur_read(pk, cur, 12);
-    if (cur.panic) return ST_REF_PANIC;
-    if (unused != 0) return ST_INVALID_HEADER;
-    uint32_t hb = cur_read(pk, cur, 4);
-    if (cur.panic) return ST_REF_PANIC;
-    const uint32_t partial = hb >> 3;
-    uint32_t shift = (hb >> 1) & 3u;
-    if (shift == 3u) return ST_INVALID_SHIFT;
-    const uint32_t escape = hb & 1u;
-    uint32_t chan_bits = cfg.bit_depth - shift * 8u + (stereo ? 1u : 0u);
-    uint32_t n = ns;
-    if (partial) {
-        n = cur_read(pk, cur, 16) << 16;
-        n |= cur_read(pk, cur, 16);
-        if (cur.panic) return ST_REF_PANIC;
-    }
-    // numSamples > frame_length: every later path re-slices a frame_length buffer and panics
-    // (golomb.go:155, decoder.go:328, :506)
-    const bool n_too_big = n > cfg.frame_length;
-    uint32_t mix_bits = 0;
-    int32_t mix_res = 0;
-    uint32_t shift_bitpos = 0;
-    int32_t *dst_u = scratch_lane + (size_t)chan_idx * cfg.frame_length * 32u;
-    int32_t *dst_v = dst_u + (size_t)cfg.frame_length * 32u;
-    if (!escape) {
-        mix_bits = cur_read(pk, cur, 8);
-        mix_res = (int32_t)(int8_t)cur_read(pk, cur, 8);
-        ChanHdr hu, hv;
-        read_chan_hdr(pk, cur, hu);
-        if (stereo) read_chan_hdr(pk, cur, hv);
-        if (cur.panic) return ST_REF_PANIC;
-        shift_bitpos = cur.bp;
-        if (shift != 0) cur.bp += shift * 8u * n * (stereo ? 2u : 1u);
-        if (n_too_big) return ST_REF_PANIC;
-        BitRes br;
-        br.init(pk, cur.bp);
-        int32_t st = decode_channel(pk, cfg, br, cur.bp, hu, n, chan_bits, dst_u);
-        if (st != ST_OK) return st == ST_REF_PANIC ? st : (st | ((stereo ? ENT_U : ENT_MONO) << 12));
-        if (stereo) {
-            st = decode_channel(pk, cfg, br, cur.bp, hv, n, chan_bits, dst_v);
-            if (st != ST_OK) return st == ST_REF_PANIC ? st : (st | (ENT_V << 12));
-        }
-    } else {
-        if (stereo) chan_bits = cfg.bit_depth;  // decoder.go:388
-        if (n_too_big) return ST_REF_PANIC;
-        if (n > 0) {
-            // every Read needs Pos+3 <= cap; positions only grow, so checking the last one is enough
-            const uint32_t per = chan_bits * (stereo ? 2u : 1u);
-            const uint32_t last_nb = chan_bits <= 16u ? chan_bits : chan_bits - 16u;
-            const uint32_t bp_last = cur.bp + n * per - last_nb;
-            if ((bp_last >> 3) + 3u > pk.size + 4u) return ST_REF_PANIC;
-            BitRes br;
-            br.init(pk, cur.bp);
+// ====================================================================================================
+// ENTROPY warp
+// ====================================================================================================
+constexpr uint32_t FULL_MASK = 0xffffffffu;
+
+// What one lane needs to produce one stream (a channel of a compressed element, or the raw samples of an
+// escape element).
+struct StreamSpec {
+    bool active;      // this lane takes part
+    bool escape;      // raw samples instead of Golomb codes
+    uint32_t n;
+    uint32_t chan_bits;
+    uint32_t pb_factor;
+    uint32_t meta;         // job meta word for the consumer
+    uint32_t coef_bitpos;  // where the consumer finds the 16-bit coefficients
+};
+
+// Produce one stream for consumer `cons`: ceil(nmax/32) ring slots (at least one: it carries the job).
+// For an interleaved escape pair both consumers' slots are filled in the same pass.
+__device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int cons, uint32_t *seq, const Packet &pk,
+                                               const DevConfig &cfg, BitReader &br, uint32_t &bp, int32_t &st,
+                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair) {
+    bool active = sp.active && st == ST_OK;
+    const uint32_t nmax = __reduce_max_sync(FULL_MASK, active ? sp.n : 0u);
+    const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
+    Entropy e;
+    e.mean = cfg.mb;
+    e.zmode = 0;
+    e.zrun = 0;
+    e.pb = (cfg.pb * sp.pb_factor) / 4u;  // SetAGParams, decoder.go:296-300
+    e.kb = cfg.kb;
+    e.wb = shl_go(1u, cfg.kb) - 1u;
+    e.max_size = sp.chan_bits;
+    e.size8 = pk.size * 8u;
 #pragma unroll 1
-            for (uint32_t i = 0; i < n; i++) {
-                dst_u[(size_t)i * 32u] = escape_sample(br, chan_bits);
-                if (stereo) dst_v[(size_t)i * 32u] = escape_sample(br, chan_bits);
-            }
-            cur.bp += n * per;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
+        mbar_wait(&sm.empty_bar[cons][slot], par ^ 1u);
+        uint32_t slot2 = 0;
+        if (pair) {
+            slot2 = seq[1] % RING_SLOTS;
+            mbar_wait(&sm.empty_bar[1][slot2], ((seq[1] / RING_SLOTS) & 1u) ^ 1u);
         }
-        shift = 0;
+        if (c == 0) {
+            sm.job[cons][slot][0][lane] = sp.n;
+            sm.job[cons][slot][1][lane] = active ? sp.meta : (uint32_t)JOB_INACTIVE;
+            sm.job[cons][slot][2][lane] = sp.coef_bitpos;
+            sm.job[cons][slot][3][lane] = nmax;
+            if (pair) {
+                sm.job[1][slot2][0][lane] = sp2.n;
+                sm.job[1][slot2][1][lane] = active ? sp2.meta : (uint32_t)JOB_INACTIVE;
+                sm.job[1][slot2][2][lane] = sp2.coef_bitpos;
+                sm.job[1][slot2][3][lane] = nmax;
+            }
+        }
+        int32_t *dst = &sm.ring[cons][slot][0][lane];
+        int32_t *dst2 = &sm.ring[1][slot2][0][lane];
+#pragma unroll 1
+        for (uint32_t j = 0; j < CHUNK; j++) {
+            const uint32_t i = c * CHUNK + j;
+            int32_t r = 0, r2 = 0;
+            // keep the staged window ahead of the reader: 16 samples eat at most 16 x 67 bits = 9 chunks, and
+            // what is consumed now was requested at least one such period ago
+            if ((j & 15u) == 0 && active) br.top_up();
+            if (active && i < sp.n) {
+                br.begin_sample();
+                if (sp.escape) {
+                    r = escape_sample(br, sp.chan_bits);
+                    if (pair) r2 = escape_sample(br, sp.chan_bits);
+                } else if (!entropy_next(pk, br, bp, e, i, sp.n, r, st)) {
+                    active = false;
+                    r = 0;
+                }
+            }
+            dst[j * 32] = r;
+            if (pair) dst2[j * 32] = r2;
+        }
+        mbar_arrive(&sm.full_bar[cons][slot]);
+        seq[cons]++;
+        if (pair) {
+            mbar_arrive(&sm.full_bar[1][slot2]);
+            seq[1]++;
+        }
     }
-    const uint32_t out_chan = (uint32_t)k_layout[cfg.num_channels - 1][chan_idx];
-    // dst := out[off:off+W:off+W] past cap(out), matrix.go:44 (only when a pair is mapped onto the last channel)
-    if (n > 0 && out_chan + (stereo ? 2u : 1u) > cfg.num_channels && n == cfg.frame_length) return ST_REF_PANIC;
-    OpDesc op;
-    op.n = n;
-    op.shift_bitpos = shift_bitpos;
-    op.kind = stereo ? 2 : 1;
-    op.out_chan = (uint8_t)out_chan;
-    op.slot = (uint8_t)chan_idx;
-    op.shift = (uint8_t)shift;
-    op.mix_bits = (uint8_t)mix_bits;
-    op.mix_res = (int8_t)mix_res;
-    op.pad_ = 0;
-    desc->ops[nops++] = op;
-    ns = n;
-    return ST_OK;
 }
 
-// decodePacketInto, decoder.go:133-207.
-__global__ void __launch_bounds__(32) alac_decode_kernel(const uint8_t *__restrict__ packed,
-                                                         const uint64_t *__restrict__ offsets,
-                                                         const uint32_t *__restrict__ sizes, uint32_t npackets,
-                                                         DevConfig cfg, int32_t *__restrict__ scratch,
-                                                         PacketDesc *__restrict__ descs,
-                                                         uint32_t *__restrict__ out_bytes,
-                                                         int32_t *__restrict__ status) {
-    const uint32_t pidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pidx >= npackets) return;
-    const uint32_t group = pidx >> 5, lane = pidx & 31u;
-    Packet pk{packed + offsets[pidx], sizes[pidx]};
-    PacketDesc *desc = descs + pidx;
-    int32_t *scratch_lane = scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+// Parsed element header of one lane (decodeSCE/decodeCPE up to the entropy stage, decoder.go:210-300, :348-460).
+struct ElemHdr {
+    bool have;    // an audio element is ready to be streamed
+    bool stereo;
+    bool escape;
+    uint32_t n, chan_bits, shift, mix_bits, shift_bitpos, chan_idx;
+    int32_t mix_res;
+    uint32_t mode[2], den[2], pbf[2], num[2], coef_bitpos[2];
+};
 
-    Cursor cur{0, false};
-    uint32_t ns = cfg.frame_length, chan_idx = 0, nops = 0;
-    int32_t st = ST_OK;
-    if (pk.size > 0x0FFFFFFFu) st = ST_REF_PANIC;  // bit positions are 32-bit here
+// One channel header: mode/denShift, pbFactor/num, num x 16-bit coefficients (decoder.go:275-286). The
+// coefficients are not copied: the predictor warp reads them from the packet itself.
+__device__ __forceinline__ void read_chan_hdr(const Packet &pk, Cursor &c, ElemHdr &h, int ch) {
+    uint32_t hb = cur_read(pk, c, 8);
+    h.mode[ch] = hb >> 4;
+    h.den[ch] = hb & 0xfu;
+    hb = cur_read(pk, c, 8);
+    h.pbf[ch] = hb >> 5;
+    h.num[ch] = hb & 0x1fu;
+    h.coef_bitpos[ch] = c.bp;
+    if (h.num[ch] > 0) {  // every Read(16) needs Pos+3 <= cap; the last one binds
+        const uint32_t last = c.bp + 16u * (h.num[ch] - 1u);
+        if ((last >> 3) + 3u > pk.size + 4u) c.panic = true;
+        c.bp += 16u * h.num[ch];
+    }
+}
+
+// Advance one lane through DSE/FIL/END until the next SCE/LFE/CPE header is parsed (decodePacketInto,
+// decoder.go:142-203, and the header part of decodeSCE/decodeCPE). Sets h.have, or finishes the lane
+// (parsing = false) with st.
+__device__ __forceinline__ void parse_to_next_element(const Packet &pk, const DevConfig &cfg, Cursor &cur, uint32_t chan_idx,
+                                                      uint32_t ns, bool &parsing, int32_t &st, ElemHdr &h) {
+    h.have = false;
 #pragma unroll 1
-    while (st == ST_OK) {
+    while (parsing) {
         if ((cur.bp >> 3) >= pk.size) {  // PastEnd, decoder.go:143-145
             st = ST_BITSTREAM_OVERRUN;
+            parsing = false;
             break;
         }
         const uint32_t tag = cur_read_small(pk, cur, 3);
-        if (cur.panic) { st = ST_REF_PANIC; break; }
-        if (tag == 0 || tag == 3) {
-            st = decode_element(pk, cfg, cur, false, chan_idx, ns, scratch_lane, desc, nops);
-            if (st != ST_OK) { st |= CTX_SCE << 8; break; }
-            chan_idx += 1;
-        } else if (tag == 1) {
-            if (chan_idx + 2 > cfg.num_channels) break;  // decoder.go:163-165
-            st = decode_element(pk, cfg, cur, true, chan_idx, ns, scratch_lane, desc, nops);
-            if (st != ST_OK) { st |= CTX_CPE << 8; break; }
-            chan_idx += 2;
+        if (cur.panic) { st = ST_REF_PANIC; parsing = false; break; }
+        if (tag == 0 || tag == 3 || tag == 1) {
+            const bool stereo = tag == 1;
+            if (stereo && chan_idx + 2 > cfg.num_channels) { parsing = false; break; }  // decoder.go:163-165
+            const int32_t ctx = (stereo ? CTX_CPE : CTX_SCE) << 8;
+            (void)cur_read_small(pk, cur, 4);
+            const uint32_t unused = cur_read(pk, cur, 12);
+            if (cur.panic) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+            if (unused != 0) { st = ST_INVALID_HEADER | ctx; parsing = false; break; }
+            const uint32_t hb = cur_read(pk, cur, 4);
+            if (cur.panic) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+            const uint32_t partial = hb >> 3;
+            h.shift = (hb >> 1) & 3u;
+            if (h.shift == 3u) { st = ST_INVALID_SHIFT | ctx; parsing = false; break; }
+            h.escape = (hb & 1u) != 0;
+            h.stereo = stereo;
+            h.chan_idx = chan_idx;
+            h.chan_bits = cfg.bit_depth - h.shift * 8u + (stereo ? 1u : 0u);
+            h.n = ns;
+            if (partial) {
+                h.n = cur_read(pk, cur, 16) << 16;
+                h.n |= cur_read(pk, cur, 16);
+                if (cur.panic) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+            }
+            h.mix_bits = 0;
+            h.mix_res = 0;
+            h.shift_bitpos = 0;
+            // numSamples > frame_length: every later path re-slices a frame_length buffer and panics
+            // (golomb.go:155, decoder.go:328, :506)
+            const bool n_too_big = h.n > cfg.frame_length;
+            if (!h.escape) {
+                h.mix_bits = cur_read(pk, cur, 8);
+                h.mix_res = (int32_t)(int8_t)cur_read(pk, cur, 8);
+                read_chan_hdr(pk, cur, h, 0);
+                if (stereo) read_chan_hdr(pk, cur, h, 1);
+                if (cur.panic) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+                h.shift_bitpos = cur.bp;
+                if (h.shift != 0) cur.bp += h.shift * 8u * h.n * (stereo ? 2u : 1u);
+                if (n_too_big) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+            } else {
+                if (stereo) h.chan_bits = cfg.bit_depth;  // decoder.go:388
+                if (n_too_big) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+                if (h.n > 0) {
+                    // every Read needs Pos+3 <= cap; positions only grow, so checking the last one is enough
+                    const uint32_t per = h.chan_bits * (stereo ? 2u : 1u);
+                    const uint32_t last_nb = h.chan_bits <= 16u ? h.chan_bits : h.chan_bits - 16u;
+                    const uint32_t bp_last = cur.bp + h.n * per - last_nb;
+                    if ((bp_last >> 3) + 3u > pk.size + 4u) { st = ST_REF_PANIC | ctx; parsing = false; break; }
+                }
+            }
+            h.have = true;
+            break;
         } else if (tag == 2 || tag == 5) {
             st = ST_UNSUPPORTED_ELEMENT;
-            break;
+            parsing = false;
         } else if (tag == 4) {  // skipDSE, decoder.go:553-574
             (void)cur_read_small(pk, cur, 4);
             const uint32_t align = cur_read_one(pk, cur);
             uint32_t count = cur_read_small(pk, cur, 8);
             if (count == 255) count += cur_read_small(pk, cur, 8);
-            if (cur.panic) { st = ST_REF_PANIC | (CTX_DSE << 8); break; }
+            if (cur.panic) { st = ST_REF_PANIC | (CTX_DSE << 8); parsing = false; break; }
             if (align) cur.bp = (cur.bp + 7u) & ~7u;
             cur.bp += count * 8u;
-            if ((cur.bp >> 3) >= pk.size) { st = ST_BITSTREAM_OVERRUN | (CTX_DSE << 8); break; }
+            if ((cur.bp >> 3) >= pk.size) { st = ST_BITSTREAM_OVERRUN | (CTX_DSE << 8); parsing = false; }
         } else if (tag == 6) {  // skipFIL, decoder.go:538-551
             uint32_t count = cur_read_small(pk, cur, 4);
             if (count == 15) count += cur_read_small(pk, cur, 8) - 1u;
-            if (cur.panic) { st = ST_REF_PANIC | (CTX_FIL << 8); break; }
+            if (cur.panic) { st = ST_REF_PANIC | (CTX_FIL << 8); parsing = false; break; }
             cur.bp += count * 8u;
-            if ((cur.bp >> 3) >= pk.size) { st = ST_BITSTREAM_OVERRUN | (CTX_FIL << 8); break; }
+            if ((cur.bp >> 3) >= pk.size) { st = ST_BITSTREAM_OVERRUN | (CTX_FIL << 8); parsing = false; }
         } else {  // END, decoder.go:192-195
-            break;
+            parsing = false;
         }
-        if (chan_idx >= cfg.num_channels) break;  // decoder.go:200-202
     }
-    desc->status = st;
-    desc->n_final = ns;
-    desc->nops = nops;
-    status[pidx] = st;
-    out_bytes[pidx] = st == ST_OK ? ns * cfg.num_channels * cfg.bps : 0u;
+}
+
+__device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
+                                             const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
+                                             uint32_t npackets, const DevConfig &cfg, PacketDesc *__restrict__ descs,
+                                             uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status) {
+    const uint32_t pidx = blockIdx.x * 32u + lane;
+    const bool valid = pidx < npackets;
+    Packet pk{packed, 0};
+    if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
+    PacketDesc *desc = descs + pidx;
+    const uint32_t fifo_addr = smem_u32(&sm.fifo[0][lane]);
+
+    Cursor cur{0, false};
+    uint32_t ns = cfg.frame_length, chan_idx = 0, nops = 0;
+    int32_t st = ST_OK;
+    bool parsing = valid;
+    if (valid && pk.size > 0x0FFFFFFFu) { st = ST_REF_PANIC; parsing = false; }  // bit positions are 32-bit here
+    uint32_t seq[2] = {0, 0};
+    BitReader br;
+    br.fifo = fifo_addr;
+
+#pragma unroll 1
+    for (;;) {
+        ElemHdr h;
+        h.have = false;
+        if (parsing) parse_to_next_element(pk, cfg, cur, chan_idx, ns, parsing, st, h);
+        if (!__any_sync(FULL_MASK, h.have)) break;
+        const int32_t ctx = (h.stereo ? CTX_CPE : CTX_SCE) << 8;
+        StreamSpec s0, s1;
+        s0.active = h.have;
+        s1.active = h.have && h.stereo;
+        s0.escape = s1.escape = h.escape;
+        s0.n = s1.n = h.n;
+        s0.chan_bits = s1.chan_bits = h.chan_bits;
+        if (h.have) {
+            if (!h.escape) {
+                // DynDecomp entry: input := Buf[Pos:] (golomb.go:149) and the first read32bit when Pos > Size
+                const uint32_t pos = cur.bp >> 3;
+                if (pos > pk.size + 4u || (h.n > 0 && pos > pk.size)) st = ST_REF_PANIC | ctx;
+                for (int c = 0; c < 2; c++) {
+                    StreamSpec &s = c ? s1 : s0;
+                    const uint32_t ord = h.num[c];
+                    const bool reg_path = ord == 0 || ord == 31 || (ord >= 4 && ord <= 6) || ord == 8;
+                    s.pb_factor = h.pbf[c];
+                    s.meta = job_meta(reg_path ? JOB_REG : JOB_GENERIC, ord, h.den[c], h.mode[c], h.chan_bits, h.chan_idx + c);
+                    s.coef_bitpos = h.coef_bitpos[c];
+                }
+            } else {
+                s0.pb_factor = s1.pb_factor = 0;
+                s0.meta = job_meta(JOB_REG, 0, 0, 0, h.chan_bits, h.chan_idx);      // pass-through
+                s1.meta = job_meta(JOB_REG, 0, 0, 0, h.chan_bits, h.chan_idx + 1);
+                s0.coef_bitpos = s1.coef_bitpos = 0;
+            }
+            if (st == ST_OK) br.init(pk, cur.bp, fifo_addr);
+        }
+        // compressed elements: pass 0 = U (or mono), pass 1 = V; escape pairs: pass 2, one interleaved sweep
+        // feeding both consumers (decoder.go:513-533)
+        uint32_t bp = cur.bp;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; pass++) {
+            const bool esc_pair = h.have && h.stereo && h.escape;
+            const bool act = pass == 0 ? (h.have && !esc_pair) : pass == 1 ? (h.have && h.stereo && !h.escape) : esc_pair;
+            if (!__any_sync(FULL_MASK, act)) continue;
+            StreamSpec a = pass == 1 ? s1 : s0;
+            a.active = act;
+            if (pass == 1 && act && st == ST_OK) {
+                // U's predictor warm-up indexes [1..numActive] of frame_length-long slices (predictor.go:76-79),
+                // then V's DynDecomp entry: bitBuf.Buf[bitBuf.Pos:] (golomb.go:149)
+                const uint32_t pos = bp >> 3;
+                if ((h.num[0] != 0 && h.num[0] != 31 && h.num[0] >= cfg.frame_length) || pos > pk.size + 4u ||
+                    (h.n > 0 && pos > pk.size))
+                    st = ST_REF_PANIC | ctx;
+            }
+            const int32_t before = st;
+            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2);
+            if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
+                if ((st & 0xff) == ST_REF_PANIC) st |= ctx;
+                else st |= ctx | ((pass == 1 ? ENT_V : h.stereo ? ENT_U : ENT_MONO) << 12);
+            }
+        }
+        // ---- per-lane epilogue of the element: position, panics of the predictor/writer, op record ----
+        if (h.have) {
+            if (st != ST_OK) {
+                parsing = false;
+            } else {
+                if (!h.escape) cur.bp = bp;
+                else cur.bp += h.n * h.chan_bits * (h.stereo ? 2u : 1u);
+                // warm-up indexes [1..numActive] of frame_length-long slices (predictor.go:76-79)
+                const uint32_t last = h.stereo ? 1u : 0u;
+                if (!h.escape && h.num[last] != 0 && h.num[last] != 31 && h.num[last] >= cfg.frame_length) st = ST_REF_PANIC | ctx;
+                const uint32_t out_chan = (uint32_t)k_layout[cfg.num_channels - 1][h.chan_idx];
+                // dst := out[off:off+W:off+W] past cap(out), matrix.go:44 (a pair mapped onto the last channel)
+                if (st == ST_OK && h.n > 0 && out_chan + (h.stereo ? 2u : 1u) > cfg.num_channels && h.n == cfg.frame_length)
+                    st = ST_REF_PANIC | ctx;
+                if (st != ST_OK) {
+                    parsing = false;
+                } else {
+                    OpDesc op;
+                    op.n = h.n;
+                    op.shift_bitpos = h.shift_bitpos;
+                    op.kind = h.stereo ? 2 : 1;
+                    op.out_chan = (uint8_t)out_chan;
+                    op.slot = (uint8_t)h.chan_idx;
+                    op.shift = (uint8_t)(h.escape ? 0u : h.shift);
+                    op.mix_bits = (uint8_t)h.mix_bits;
+                    op.mix_res = (int8_t)h.mix_res;
+                    op.pad_ = 0;
+                    desc->ops[nops++] = op;
+                    ns = h.n;
+                    chan_idx += h.stereo ? 2u : 1u;
+                    if (chan_idx >= cfg.num_channels) parsing = false;  // decoder.go:200-202
+                }
+            }
+        }
+    }
+    BitReader::wait_all();
+    // tell both predictor warps to leave
+    for (int cons = 0; cons < 2; cons++) {
+        const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
+        mbar_wait(&sm.empty_bar[cons][slot], par ^ 1u);
+        sm.job[cons][slot][1][lane] = JOB_EXIT;
+        mbar_arrive(&sm.full_bar[cons][slot]);
+    }
+    if (valid) {
+        desc->status = st;
+        desc->n_final = ns;
+        desc->nops = nops;
+        status[pidx] = st;
+        out_bytes[pidx] = st == ST_OK ? ns * cfg.num_channels * cfg.bps : 0u;
+    }
+}
+
+// ====================================================================================================
+// PREDICTOR warps
+// ====================================================================================================
+// Order-31 pre-pass (mode != 0: UnpcBlock(pred, pred, n, nil, 31, chanBits, 0), decoder.go:306-308)
+__device__ __forceinline__ int32_t delta_step(bool on, int32_t &prev, int32_t r, uint32_t i, uint32_t cs) {
+    if (!on) return r;
+    prev = (i == 0) ? r : sext_go(r + prev, cs);
+    return prev;
+}
+
+struct Job {
+    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax;
+};
+
+// Register predictor: orders 4/5/6/8 with int32 coefficients (unpcBlock4/5/6/8, predictor.go:99-618), plus
+// order 0 (copy, also escape pass-through) and order 31 (running sum), predictor.go:55-72. T = taps kept.
+template <int T>
+__device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
+                                           const Job &jb, bool active, int32_t *__restrict__ dst) {
+    const uint32_t cs = 32u - jb.chan_bits;
+    const uint32_t den = jb.den;
+    const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
+    const int32_t order = (int32_t)jb.order;
+    const bool fir_order = order == 4 || order == 5 || order == 6 || order == 8;
+    const uint32_t fir_from = fir_order ? (uint32_t)order + 1u : 0xffffffffu;
+    const bool acc = order != 0;  // warm-up / order 31 accumulate; order 0 copies
+    const bool mode = jb.mode != 0;
+    int32_t c[T], h[T + 1], wgt[T];
+    bool in_tap[T];
+#pragma unroll
+    for (int j = 0; j < T; j++) {
+        const bool in = fir_order && j < order;
+        c[j] = (active && in) ? (int32_t)(int16_t)pk_bits(pk, jb.coef_bitpos + 16u * (uint32_t)j, 16) : 0;
+        wgt[j] = in ? order - j : 0;
+        in_tap[j] = in;
+    }
+#pragma unroll
+    for (int j = 0; j <= T; j++) h[j] = 0;
+    int32_t dprev = 0;
+    const uint32_t nchunks = max(1u, (jb.nmax + CHUNK - 1) / CHUNK);
+#pragma unroll 1
+    for (uint32_t ck = 0; ck < nchunks; ck++) {
+        const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        if (ck > 0) mbar_wait(&sm.full_bar[cons][slot], par);
+        const int32_t *src = &sm.ring[cons][slot][0][lane];
+#pragma unroll 4
+        for (uint32_t j = 0; j < CHUNK; j++) {
+            const uint32_t i = ck * CHUNK + j;
+            int32_t r = src[j * 32];
+            if (active && i < jb.n) {
+                r = delta_step(mode, dprev, r, i, cs);
+                int32_t top;
+                if (T == 8) top = (order == 4) ? h[4] : (order == 5) ? h[5] : (order == 6) ? h[6] : h[8];
+                else top = (order == 4) ? h[4] : (order == 5) ? h[5] : h[6];
+                int32_t d[T];
+                int32_t sum = den_half;
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    d[t] = top - h[t];
+                    sum -= c[t] * d[t];
+                }
+                const int32_t fir = sext_go(r + top + (sum >> den), cs);
+                const int32_t warm = (i == 0 || !acc) ? r : sext_go(r + h[0], cs);
+                const bool is_fir = i >= fir_from;
+                const int32_t x = is_fir ? fir : warm;
+                // sign-LMS adaptation on the residual's sign
+                bool alive = is_fir && (r != 0);
+                const int32_t smask = r >> 31;  // 0 / -1
+                const int32_t thr = 1 + smask;  // continue while (D ^ smask) >= thr  <=>  D > 0 (r>0) / D < 0 (r<0)
+                int32_t D = r;
+#pragma unroll
+                for (int t = T - 1; t >= 0; t--) {
+                    const int32_t sg = sign_of(d[t]);
+                    const int32_t sgn = (sg ^ smask) - smask;  // sg for r>0, -sg for r<0
+                    const bool act = alive && in_tap[t];
+                    if (act) c[t] -= sgn;
+                    if (t > 0) {
+                        const int32_t term = (sgn * d[t]) >> den;
+                        D -= wgt[t] * term;  // wgt == 0 for masked taps
+                        alive = alive && (!in_tap[t] || ((D ^ smask) >= thr));
+                    }
+                }
+#pragma unroll
+                for (int t = T; t > 0; t--) h[t] = h[t - 1];
+                h[0] = x;
+                dst[(size_t)i * 32u] = x;
+            }
+        }
+        mbar_arrive(&sm.empty_bar[cons][slot]);
+        seq++;
+    }
+}
+
+// Any mix of orders in the warp, including the int16-wrapping ones: unpcBlockGeneral, predictor.go:623-684,
+// with per-lane coefficient width (int32 kept for 4/5/6/8 as the reference's specialised loops do).
+__device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
+                                            const Job &jb, bool active, int32_t *__restrict__ dst) {
+    const uint32_t cs = 32u - jb.chan_bits;
+    const uint32_t den = jb.den;
+    const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
+    const int32_t order = (int32_t)jb.order;
+    const bool wrap16 = jb.kind == JOB_GENERIC;
+    const bool mode = jb.mode != 0;
+    int32_t coef[32];
+    int32_t hist[32];  // ring: out[i] at hist[i & 31]
+#pragma unroll 1
+    for (int k = 0; k < 32; k++) {
+        coef[k] = (active && k < order && order != 31) ? (int32_t)(int16_t)pk_bits(pk, jb.coef_bitpos + 16u * (uint32_t)k, 16) : 0;
+        hist[k] = 0;
+    }
+    int32_t dprev = 0;
+    const uint32_t nchunks = max(1u, (jb.nmax + CHUNK - 1) / CHUNK);
+#pragma unroll 1
+    for (uint32_t ck = 0; ck < nchunks; ck++) {
+        const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        if (ck > 0) mbar_wait(&sm.full_bar[cons][slot], par);
+        const int32_t *src = &sm.ring[cons][slot][0][lane];
+#pragma unroll 1
+        for (uint32_t j = 0; j < CHUNK; j++) {
+            const uint32_t i = ck * CHUNK + j;
+            int32_t r = src[j * 32];
+            if (active && i < jb.n) {
+                r = delta_step(mode, dprev, r, i, cs);
+                int32_t x;
+                if (i == 0 || order == 0) x = r;
+                else if (order == 31 || (int32_t)i <= order) x = sext_go(r + hist[(i - 1) & 31u], cs);
+                else {
+                    const int32_t top = hist[(i - (uint32_t)order - 1u) & 31u];
+                    int32_t sum1 = 0;
+#pragma unroll 1
+                    for (int32_t k = 0; k < order; k++) sum1 += coef[k] * (hist[(i - 1u - (uint32_t)k) & 31u] - top);
+                    x = sext_go(r + top + ((sum1 + den_half) >> den), cs);
+                    int32_t del0 = r;
+                    if (r != 0) {
+                        const int32_t s = r > 0 ? 1 : -1;
+#pragma unroll 1
+                        for (int32_t k = order - 1; k >= 0; k--) {
+                            const int32_t dd = top - hist[(i - 1u - (uint32_t)k) & 31u];
+                            const int32_t sgn = s * sign_of(dd);
+                            int32_t nc = coef[k] - sgn;
+                            if (wrap16) nc = (int32_t)(int16_t)nc;
+                            coef[k] = nc;
+                            del0 -= (order - k) * ((sgn * dd) >> den);
+                            if (s > 0 ? del0 <= 0 : del0 >= 0) break;
+                        }
+                    }
+                }
+                hist[i & 31u] = x;
+                dst[(size_t)i * 32u] = x;
+            }
+        }
+        mbar_arrive(&sm.empty_bar[cons][slot]);
+        seq++;
+    }
+}
+
+__device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int cons, const uint8_t *__restrict__ packed,
+                                               const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
+                                               uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch) {
+    const uint32_t pidx = blockIdx.x * 32u + lane;
+    const bool valid = pidx < npackets;
+    Packet pk{packed, 0};
+    if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
+    int32_t *scratch_lane = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u + lane;
+    uint32_t seq = 0;
+#pragma unroll 1
+    for (;;) {
+        const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        mbar_wait(&sm.full_bar[cons][slot], par);
+        Job jb;
+        jb.n = sm.job[cons][slot][0][lane];
+        const uint32_t meta = sm.job[cons][slot][1][lane];
+        jb.coef_bitpos = sm.job[cons][slot][2][lane];
+        jb.nmax = sm.job[cons][slot][3][lane];
+        jb.kind = meta & 3u;
+        if (jb.kind == JOB_EXIT) break;  // written for every lane
+        jb.order = (meta >> 2) & 31u;
+        jb.den = (meta >> 7) & 15u;
+        jb.mode = (meta >> 11) & 1u;
+        jb.chan_bits = (meta >> 12) & 63u;
+        jb.slot = (meta >> 18) & 7u;
+        jb.nmax = __shfl_sync(FULL_MASK, jb.nmax, 0);
+        const bool active = valid && jb.kind != JOB_INACTIVE;
+        int32_t *dst = scratch_lane + (size_t)jb.slot * cfg.frame_length * 32u;
+        const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
+        const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
+        if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst);
+        else if (any8) stream_reg<8>(sm, lane, cons, seq, pk, jb, active, dst);
+        else stream_reg<6>(sm, lane, cons, seq, pk, jb, active, dst);
+    }
+}
+
+// decodePacketInto for 32 packets per CTA, decoder.go:133-207.
+__global__ void __launch_bounds__(DEC_THREADS) alac_decode_kernel(const uint8_t *__restrict__ packed,
+                                                                  const uint64_t *__restrict__ offsets,
+                                                                  const uint32_t *__restrict__ sizes, uint32_t npackets,
+                                                                  DevConfig cfg, int32_t *__restrict__ scratch,
+                                                                  PacketDesc *__restrict__ descs,
+                                                                  uint32_t *__restrict__ out_bytes,
+                                                                  int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) uint8_t dec_smem[];
+    DecShared &sm = *reinterpret_cast<DecShared *>(dec_smem);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 2; c++)
+            for (int s = 0; s < RING_SLOTS; s++) {
+                mbar_init(&sm.full_bar[c][s], 32);
+                mbar_init(&sm.empty_bar[c][s], 32);
+            }
+    }
+    __syncthreads();
+    // rotate the roles over the warp slots so co-resident CTAs do not stack their entropy warps on one SMSP
+    const uint32_t role = (warp + blockIdx.x) % 3u;
+    if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
+    else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch);
 }
 
 // ---- stage 3 ---------------------------------------------------------------------------------------
