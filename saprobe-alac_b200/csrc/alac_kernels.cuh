@@ -150,6 +150,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+// Optional role timing (clock64 per role, lane 0): [cta][8] = E total, E wait-empty, E top-up, P0 total, P0 wait,
+// P1 total, P1 wait, unused. Enabled by pointing g_role_cycles at a buffer (alacb200_debug_role_cycles).
+__device__ unsigned long long *g_role_cycles = nullptr;
+struct RoleTimer {
+    unsigned long long *slot;
+    unsigned long long acc[3] = {0, 0, 0};
+    __device__ __forceinline__ RoleTimer(uint32_t lane, int base) {
+        unsigned long long *b = g_role_cycles;
+        slot = (b != nullptr && lane == 0) ? b + (size_t)blockIdx.x * 8 + base : nullptr;
+    }
+    __device__ __forceinline__ unsigned long long now() const { return slot ? clock64() : 0ull; }
+    __device__ __forceinline__ void add(int k, unsigned long long t0) { if (slot) acc[k] += clock64() - t0; }
+    __device__ __forceinline__ void flush(int n) { if (slot) for (int k = 0; k < n; k++) slot[k] = acc[k]; }
+};
+
 // ---- geometry of one decode CTA ---------------------------------------------------------------------
 // 3 warps, 32 packets: one ENTROPY warp (lane = packet) walks the grammar and the Golomb stream and hands
 // residuals, 32 samples at a time, through a shared-memory ring to two PREDICTOR warps (lane = packet):
@@ -163,7 +178,7 @@ constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged pe
 struct DecShared {
     int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (32 KB)
     uint32_t job[2][RING_SLOTS][4][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax
-    uint4 fifo[FIFO_CHUNKS][32];             // compressed bytes staged by cp.async, [chunk][lane]       (16 KB)
+    uint4 fifo[32][FIFO_CHUNKS + 1];         // compressed bytes staged by cp.async, [lane][chunk] (+1: bank skew)
     uint64_t full_bar[2][RING_SLOTS];
     uint64_t empty_bar[2][RING_SLOTS];
 };
@@ -177,35 +192,44 @@ __device__ __forceinline__ uint32_t job_meta(uint32_t kind, uint32_t order, uint
 
 // ---- bit reader of the entropy warp -----------------------------------------------------------------
 // The compressed packet is staged into shared memory with 128-bit cp.async (zero-filled past the packet
-// end = the reference's zero padding, bitbuffer.go:36-51) one ring-chunk period ahead of its use; the
-// hot loop then needs one LDS per sample, issued at the top of the iteration, and a branch-free refill.
+// end = the reference's zero padding, bitbuffer.go:36-51) at least one half-chunk period ahead of its use;
+// the hot loop then needs one LDS per sample, issued at the top of the iteration, and a branch-free refill.
+constexpr uint32_t FIFO_LANE_BYTES = FIFO_CHUNKS * 16 + 16;  // 528: +16 skews the lanes over the banks
+
+// clz(x) for x != 0 in ONE instruction (FLO.U32.SH); 0xffffffff for x == 0
+__device__ __forceinline__ uint32_t clz_nz(uint32_t x) {
+    uint32_t r;
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 struct BitReader {
     const uint8_t *gbase;  // 16-byte aligned global address at or below the packet start
     uint32_t end_rel;      // packet end, bytes from gbase
-    uint32_t fifo;         // shared address of fifo[0][lane]
+    uint32_t fifo;         // shared address of this lane's window (FIFO_CHUNKS x 16 bytes)
     uint32_t req;          // next 16-byte chunk to request
-    uint32_t q;            // word index (from gbase) held in hi; lo holds q+1
+    uint32_t qn;           // index (32-bit words from gbase) of the next word to load; hi = qn-2, lo = qn-1
     uint32_t hi, lo, nxt;  // big-endian-converted words
     uint32_t sh;           // bits of hi already consumed (0..31)
 
     __device__ __forceinline__ void request(uint32_t c) {
         const uint32_t b0 = c << 4;
-        uint32_t nbytes = b0 >= end_rel ? 0u : min(16u, end_rel - b0);
+        const uint32_t nbytes = b0 >= end_rel ? 0u : min(16u, end_rel - b0);
         const uint8_t *src = gbase + (nbytes ? b0 : 0u);
-        const uint32_t dst = fifo + ((c & (FIFO_CHUNKS - 1)) * 32u) * 16u;
+        const uint32_t dst = fifo + ((c & (FIFO_CHUNKS - 1)) << 4);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
     }
     __device__ __forceinline__ static void wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
     __device__ __forceinline__ uint32_t load(uint32_t widx) const {
-        const uint32_t a = fifo + (((widx >> 2) & (FIFO_CHUNKS - 1)) * 32u) * 16u + (widx & 3u) * 4u;
+        const uint32_t a = fifo + ((widx & (FIFO_CHUNKS * 4 - 1)) << 2);
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
         return __byte_perm(v, 0, 0x0123);
     }
-    // called once per ring chunk: land what was requested a period ago, request up to a full window ahead
+    // land what was requested a period ago, request up to a full window ahead of the reader
     __device__ __forceinline__ void top_up() {
         wait_all();
-        const uint32_t lim = ((q + 2u) >> 2) + FIFO_CHUNKS;
+        const uint32_t lim = (qn >> 2) + FIFO_CHUNKS;
         while (req < lim) request(req++);
     }
     __device__ __forceinline__ void init(const Packet &pk, uint32_t bp, uint32_t fifo_addr) {
@@ -215,7 +239,7 @@ struct BitReader {
         end_rel = mis + pk.size;
         fifo = fifo_addr;
         const uint32_t abp = bp + mis * 8u;
-        q = abp >> 5;
+        const uint32_t q = abp >> 5;
         sh = abp & 31u;
         wait_all();  // nothing of a previous element may still be landing in the window
         req = q >> 2;
@@ -224,33 +248,29 @@ struct BitReader {
         wait_all();
         hi = load(q);
         lo = load(q + 1u);
-        nxt = load(q + 2u);
+        qn = q + 2u;
+        nxt = load(qn);
     }
     // top of every sample iteration: (re)load the word after lo; its latency hides behind the decode
-    __device__ __forceinline__ void begin_sample() { nxt = load(q + 2u); }
+    __device__ __forceinline__ void begin_sample() { nxt = load(qn); }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, sh); }
-    // first consume of an iteration: branch-free, at most one refill from the preloaded nxt
-    __device__ __forceinline__ void consume_hot(uint32_t nb) {
-        sh += nb;
-        const bool need = sh >= 32u;
+    // first consume of an iteration, branch-free: sh2 = sh + bits consumed, must be < 64
+    __device__ __forceinline__ void commit(uint32_t sh2) {
+        const bool need = sh2 >= 32u;
         hi = need ? lo : hi;
         lo = need ? nxt : lo;
-        q += need ? 1u : 0u;
-        sh -= need ? 32u : 0u;
-        if (sh >= 32u) consume_more();
+        qn += need ? 1u : 0u;
+        sh = sh2 & 31u;
     }
-    // any further consume: reloads as it goes
-    __device__ __forceinline__ void consume_more() {
-        while (sh >= 32u) {
-            hi = lo;
-            lo = load(q + 2u);
-            q += 1u;
-            sh -= 32u;
-        }
-    }
+    // any other consume: reloads as it goes
     __device__ __forceinline__ void consume_slow(uint32_t nb) {
         sh += nb;
-        consume_more();
+        while (sh >= 32u) {
+            hi = lo;
+            lo = load(qn);
+            qn += 1u;
+            sh -= 32u;
+        }
     }
 };
 
@@ -262,7 +282,49 @@ struct Entropy {
     uint32_t size8;     // packet size in bits
 };
 
-// Decodes the residual of sample index i (0-based) of n. Returns false and sets st on error.
+// After a decoded code: does the decoder enter zero-run mode (golomb.go:220)?
+__device__ __forceinline__ bool zero_run_due(uint32_t mean, uint32_t i, uint32_t n) { return (mean << 2) < 512u && i + 1u < n; }
+
+// Zero run: dynGet, golomb.go:112-144 and :221-245. Returns false and sets st on error.
+__device__ __forceinline__ bool zero_run_start(const Packet &pk, BitReader &br, uint32_t &bp, Entropy &e, uint32_t i,
+                                               uint32_t n, int32_t &st) {
+    e.zmode = 1;
+    int32_t k32 = __clz((int32_t)e.mean) - 24 + (int32_t)((e.mean + 16u) >> 6);
+    if (k32 < 0) k32 = 0;
+    const uint32_t mz = (shl_go(1u, (uint32_t)k32) - 1u) & e.wb;
+    if ((bp >> 3) > pk.size) { st = ST_REF_PANIC; return false; }
+    const uint32_t w2 = br.window();
+    const uint32_t pre = (uint32_t)__clz((int32_t)~w2);
+    uint32_t run, nb;
+    if (pre >= 9u) {
+        run = (w2 << 9) >> 16;
+        nb = 25u;
+    } else {
+        nb = pre + 1u;
+        const uint32_t s = shl_go(w2, nb);
+        const uint32_t val = shr_go(s, 32u - (uint32_t)k32);
+        nb += (uint32_t)k32;
+        if (val < 2u) {
+            run = pre * mz;
+            nb -= 1u;
+        } else {
+            run = pre * mz + val - 1u;
+        }
+    }
+    bp += nb;
+    br.consume_slow(nb);
+    if (i + 1u + run > n) {  // golomb.go:232-234
+        st = ST_SAMPLE_OVERRUN;
+        return false;
+    }
+    e.zrun = run;
+    if (run >= 65535u) e.zmode = 0;
+    e.mean = 0;
+    return true;
+}
+
+// The general (cold) step of DynDecomp for sample index i of n: zero-run continuation, overrun, escape
+// codes, oversized codes. Returns false and sets st on error.
 __device__ __forceinline__ bool entropy_next(const Packet &pk, BitReader &br, uint32_t &bp, Entropy &e, uint32_t i,
                                              uint32_t n, int32_t &res, int32_t &st) {
     if (e.zrun > 0) {  // inside a zero run (clear(predCoefs[count:end]), golomb.go:237)
@@ -310,7 +372,7 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitReader &br, ui
         const uint32_t nb = r + k + (big ? 1u : 0u);
         r = r * m + (big ? v - 1u : 0u);
         bp += nb;
-        br.consume_hot(nb);
+        br.consume_slow(nb);
     }
     const uint32_t nd = r + e.zmode;
     const int32_t mag = (int32_t)((nd + 1u) >> 1);
@@ -318,41 +380,7 @@ __device__ __forceinline__ bool entropy_next(const Packet &pk, BitReader &br, ui
     e.mean = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
     if (r > 0xffffu) e.mean = 0xffffu;
     e.zmode = 0;
-    if ((e.mean << 2) < 512u && i + 1u < n) {
-        // zero run: dynGet, golomb.go:112-144
-        e.zmode = 1;
-        int32_t k32 = __clz((int32_t)e.mean) - 24 + (int32_t)((e.mean + 16u) >> 6);
-        if (k32 < 0) k32 = 0;
-        const uint32_t mz = (shl_go(1u, (uint32_t)k32) - 1u) & e.wb;
-        if ((bp >> 3) > pk.size) { st = ST_REF_PANIC; return false; }
-        const uint32_t w2 = br.window();
-        const uint32_t pre = (uint32_t)__clz((int32_t)~w2);
-        uint32_t run, nb;
-        if (pre >= 9u) {
-            run = (w2 << 9) >> 16;
-            nb = 25u;
-        } else {
-            nb = pre + 1u;
-            const uint32_t s = shl_go(w2, nb);
-            const uint32_t val = shr_go(s, 32u - (uint32_t)k32);
-            nb += (uint32_t)k32;
-            if (val < 2u) {
-                run = pre * mz;
-                nb -= 1u;
-            } else {
-                run = pre * mz + val - 1u;
-            }
-        }
-        bp += nb;
-        br.consume_slow(nb);
-        if (i + 1u + run > n) {  // golomb.go:232-234
-            st = ST_SAMPLE_OVERRUN;
-            return false;
-        }
-        e.zrun = run;
-        if (run >= 65535u) e.zmode = 0;
-        e.mean = 0;
-    }
+    if (zero_run_due(e.mean, i, n)) return zero_run_start(pk, br, bp, e, i, n, st);
     return true;
 }
 
@@ -382,6 +410,8 @@ __constant__ int8_t k_layout[8][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 
 // ====================================================================================================
 constexpr uint32_t FULL_MASK = 0xffffffffu;
 
+enum : uint32_t { BUSY_ZERO_RUN = 1, BUSY_ESCAPE = 2, BUSY_LONG_CODES = 4, BUSY_DEAD = 8 };
+
 // What one lane needs to produce one stream (a channel of a compressed element, or the raw samples of an
 // escape element).
 struct StreamSpec {
@@ -398,7 +428,7 @@ struct StreamSpec {
 // For an interleaved escape pair both consumers' slots are filled in the same pass.
 __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int cons, uint32_t *seq, const Packet &pk,
                                                const DevConfig &cfg, BitReader &br, uint32_t &bp, int32_t &st,
-                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair) {
+                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, RoleTimer &rt) {
     bool active = sp.active && st == ST_OK;
     const uint32_t nmax = __reduce_max_sync(FULL_MASK, active ? sp.n : 0u);
     const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
@@ -411,10 +441,14 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
     e.wb = shl_go(1u, cfg.kb) - 1u;
     e.max_size = sp.chan_bits;
     e.size8 = pk.size * 8u;
+    // per-lane reasons to stay out of the straight-line path
+    uint32_t busy = (sp.escape ? BUSY_ESCAPE : 0u) | (cfg.kb > 22u ? BUSY_LONG_CODES : 0u) | (active ? 0u : BUSY_DEAD);
 #pragma unroll 1
     for (uint32_t c = 0; c < nchunks; c++) {
         const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
+        const unsigned long long tw = rt.now();
         mbar_wait(&sm.empty_bar[cons][slot], par ^ 1u);
+        rt.add(1, tw);
         uint32_t slot2 = 0;
         if (pair) {
             slot2 = seq[1] % RING_SLOTS;
@@ -434,25 +468,70 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
         }
         int32_t *dst = &sm.ring[cons][slot][0][lane];
         int32_t *dst2 = &sm.ring[1][slot2][0][lane];
+        // samples of this lane inside this chunk
+        const uint32_t base_i = c * CHUNK;
+        const uint32_t cnt = (active && sp.n > base_i) ? min((uint32_t)CHUNK, sp.n - base_i) : 0u;
 #pragma unroll 1
-        for (uint32_t j = 0; j < CHUNK; j++) {
-            const uint32_t i = c * CHUNK + j;
-            int32_t r = 0, r2 = 0;
-            // keep the staged window ahead of the reader: 16 samples eat at most 16 x 67 bits = 9 chunks, and
-            // what is consumed now was requested at least one such period ago
-            if ((j & 15u) == 0 && active) br.top_up();
-            if (active && i < sp.n) {
-                br.begin_sample();
-                if (sp.escape) {
-                    r = escape_sample(br, sp.chan_bits);
-                    if (pair) r2 = escape_sample(br, sp.chan_bits);
-                } else if (!entropy_next(pk, br, bp, e, i, sp.n, r, st)) {
-                    active = false;
-                    r = 0;
-                }
+        for (uint32_t half = 0; half < 2; half++) {
+            // keep the staged window ahead of the reader: 16 samples eat at most 16 x 67 bits = 9 chunks of 16
+            // bytes, and what is consumed now was requested at least one such period ago
+            if (active) {
+                const unsigned long long tt = rt.now();
+                br.top_up();
+                rt.add(2, tt);
             }
-            dst[j * 32] = r;
-            if (pair) dst2[j * 32] = r2;
+#pragma unroll 2
+            for (uint32_t jj = 0; jj < CHUNK / 2; jj++) {
+                const uint32_t j = half * (CHUNK / 2) + jj;
+                const uint32_t i = base_i + j;
+                br.begin_sample();
+                // ---- speculative decode of one ordinary code (golomb.go:172-201), straight-line ----------
+                const uint32_t w = br.window();
+                const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
+                uint32_t k = 31u - clz_nz((e.mean >> 9) + 3u);
+                k = min(k, e.kb);
+                const uint32_t mm = shl_go(1u, k) - 1u;
+                const uint32_t sfx = w << ((pre + 1u) & 31u);
+                const uint32_t v = shr_go(sfx, 32u - k);  // k == 0 (cookie kb 0) shifts by 32 -> 0
+                const bool big = v >= 2u;                 // v < 2: no suffix value, one bit goes back
+                const uint32_t nb = pre + k + (big ? 1u : 0u);
+                const uint32_t r = pre * mm + (big ? v - 1u : 0u);
+                // anything else goes through the general step: zero-run start / continuation, idle or failed
+                // lane, escape code, escape element, packet overrun, cookies whose codes can exceed one refill
+                const bool ordinary = ((e.zrun | busy) == 0u) & (j < cnt) & (pre < 9u) & (bp < e.size8);
+                int32_t res = 0, res2 = 0;
+                if (ordinary) {
+                    br.commit(br.sh + nb);  // kb <= 22 here: nb <= 31, one refill at most
+                    bp += nb;
+                    const uint32_t nd = r + e.zmode;
+                    res = (int32_t)((nd >> 1) ^ (0u - (nd & 1u)));  // == ((nd+1)>>1) * (1 - 2*(nd&1)) for nd < 2^32-1
+                    uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
+                    if (r > 0xffffu) mean2 = 0xffffu;
+                    e.mean = mean2;
+                    e.zmode = 0;
+                    // the zero-run code that follows (golomb.go:220) is read by the general step of the next sample
+                    busy |= zero_run_due(mean2, i, sp.n) ? BUSY_ZERO_RUN : 0u;
+                } else if (j < cnt && !(busy & BUSY_DEAD)) {
+                    if (sp.escape) {
+                        res = escape_sample(br, sp.chan_bits);
+                        if (pair) res2 = escape_sample(br, sp.chan_bits);
+                    } else {
+                        bool ok = true;
+                        if (busy & BUSY_ZERO_RUN) {
+                            busy &= ~BUSY_ZERO_RUN;
+                            ok = zero_run_start(pk, br, bp, e, i - 1u, sp.n, st);
+                        }
+                        if (ok) ok = entropy_next(pk, br, bp, e, i, sp.n, res, st);
+                        if (!ok) {
+                            active = false;
+                            busy |= BUSY_DEAD;  // a failed lane idles through the rest of the stream
+                            res = 0;
+                        }
+                    }
+                }
+                dst[j * 32] = res;
+                if (pair) dst2[j * 32] = res2;
+            }
         }
         mbar_arrive(&sm.full_bar[cons][slot]);
         seq[cons]++;
@@ -589,7 +668,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     PacketDesc *desc = descs + pidx;
-    const uint32_t fifo_addr = smem_u32(&sm.fifo[0][lane]);
+    const uint32_t fifo_addr = smem_u32(&sm.fifo[lane][0]);
 
     Cursor cur{0, false};
     uint32_t ns = cfg.frame_length, chan_idx = 0, nops = 0;
@@ -599,6 +678,8 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     uint32_t seq[2] = {0, 0};
     BitReader br;
     br.fifo = fifo_addr;
+    RoleTimer rt(lane, 0);
+    const unsigned long long t_start = rt.now();
 
 #pragma unroll 1
     for (;;) {
@@ -653,7 +734,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                     st = ST_REF_PANIC | ctx;
             }
             const int32_t before = st;
-            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2);
+            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
                 if ((st & 0xff) == ST_REF_PANIC) st |= ctx;
                 else st |= ctx | ((pass == 1 ? ENT_V : h.stereo ? ENT_U : ENT_MONO) << 12);
@@ -695,6 +776,14 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         }
     }
     BitReader::wait_all();
+    rt.add(0, t_start);
+    rt.flush(3);
+    if (rt.slot) {
+        uint32_t smid, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        rt.slot[7] = ((unsigned long long)smid << 8) | wid;
+    }
     // tell both predictor warps to leave
     for (int cons = 0; cons < 2; cons++) {
         const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
@@ -726,78 +815,92 @@ struct Job {
 };
 
 // Register predictor: orders 4/5/6/8 with int32 coefficients (unpcBlock4/5/6/8, predictor.go:99-618), plus
-// order 0 (copy, also escape pass-through) and order 31 (running sum), predictor.go:55-72. T = taps kept.
-template <int T>
+// order 0 (copy, also escape pass-through) and order 31 (running sum), predictor.go:55-72. T = taps kept;
+// a lane whose order is below T runs with its upper taps' history differences forced to zero, which keeps
+// their coefficients at zero and their LMS terms at zero. The body is branch-free; only the store is predicated.
+template <int T, bool MODE>
 __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
-                                           const Job &jb, bool active, int32_t *__restrict__ dst) {
+                                           const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
     const int32_t order = (int32_t)jb.order;
     const bool fir_order = order == 4 || order == 5 || order == 6 || order == 8;
     const uint32_t fir_from = fir_order ? (uint32_t)order + 1u : 0xffffffffu;
-    const bool acc = order != 0;  // warm-up / order 31 accumulate; order 0 copies
-    const bool mode = jb.mode != 0;
+    const bool copy = order == 0;  // order 0 copies; warm-up and order 31 accumulate
+    const bool mode = MODE && jb.mode != 0;
+    const uint32_t n_lane = active ? jb.n : 0u;
+    const bool sel4 = order == 4, sel5 = order == 5, sel6 = order == 6;
     int32_t c[T], h[T + 1], wgt[T];
-    bool in_tap[T];
+    uint32_t tmask[T];
 #pragma unroll
-    for (int j = 0; j < T; j++) {
-        const bool in = fir_order && j < order;
-        c[j] = (active && in) ? (int32_t)(int16_t)pk_bits(pk, jb.coef_bitpos + 16u * (uint32_t)j, 16) : 0;
-        wgt[j] = in ? order - j : 0;
-        in_tap[j] = in;
+    for (int t = 0; t < T; t++) {
+        const bool in = fir_order && t < order;
+        c[t] = (active && in) ? (int32_t)(int16_t)pk_bits(pk, jb.coef_bitpos + 16u * (uint32_t)t, 16) : 0;
+        wgt[t] = in ? order - t : 0;
+        tmask[t] = in ? 0xffffffffu : 0u;
     }
 #pragma unroll
-    for (int j = 0; j <= T; j++) h[j] = 0;
+    for (int t = 0; t <= T; t++) h[t] = 0;
     int32_t dprev = 0;
+    int32_t *outp = dst;
     const uint32_t nchunks = max(1u, (jb.nmax + CHUNK - 1) / CHUNK);
 #pragma unroll 1
     for (uint32_t ck = 0; ck < nchunks; ck++) {
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
-        if (ck > 0) mbar_wait(&sm.full_bar[cons][slot], par);
+        if (ck > 0) {
+            const unsigned long long tw = rt.now();
+            mbar_wait(&sm.full_bar[cons][slot], par);
+            rt.add(1, tw);
+        }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
-#pragma unroll 4
+#pragma unroll 8
         for (uint32_t j = 0; j < CHUNK; j++) {
             const uint32_t i = ck * CHUNK + j;
             int32_t r = src[j * 32];
-            if (active && i < jb.n) {
-                r = delta_step(mode, dprev, r, i, cs);
-                int32_t top;
-                if (T == 8) top = (order == 4) ? h[4] : (order == 5) ? h[5] : (order == 6) ? h[6] : h[8];
-                else top = (order == 4) ? h[4] : (order == 5) ? h[5] : h[6];
-                int32_t d[T];
-                int32_t sum = den_half;
-#pragma unroll
-                for (int t = 0; t < T; t++) {
-                    d[t] = top - h[t];
-                    sum -= c[t] * d[t];
-                }
-                const int32_t fir = sext_go(r + top + (sum >> den), cs);
-                const int32_t warm = (i == 0 || !acc) ? r : sext_go(r + h[0], cs);
-                const bool is_fir = i >= fir_from;
-                const int32_t x = is_fir ? fir : warm;
-                // sign-LMS adaptation on the residual's sign
-                bool alive = is_fir && (r != 0);
-                const int32_t smask = r >> 31;  // 0 / -1
-                const int32_t thr = 1 + smask;  // continue while (D ^ smask) >= thr  <=>  D > 0 (r>0) / D < 0 (r<0)
-                int32_t D = r;
-#pragma unroll
-                for (int t = T - 1; t >= 0; t--) {
-                    const int32_t sg = sign_of(d[t]);
-                    const int32_t sgn = (sg ^ smask) - smask;  // sg for r>0, -sg for r<0
-                    const bool act = alive && in_tap[t];
-                    if (act) c[t] -= sgn;
-                    if (t > 0) {
-                        const int32_t term = (sgn * d[t]) >> den;
-                        D -= wgt[t] * term;  // wgt == 0 for masked taps
-                        alive = alive && (!in_tap[t] || ((D ^ smask) >= thr));
-                    }
-                }
-#pragma unroll
-                for (int t = T; t > 0; t--) h[t] = h[t - 1];
-                h[0] = x;
-                dst[(size_t)i * 32u] = x;
+            if (MODE) {  // order-31 pre-pass on the residuals (decoder.go:306-308)
+                const int32_t dn = (i == 0) ? r : sext_go(r + dprev, cs);
+                r = mode ? dn : r;
+                dprev = r;
             }
+            int32_t top;
+            if (T == 8) top = sel4 ? h[4] : sel5 ? h[5] : sel6 ? h[6] : h[8];
+            else top = sel4 ? h[4] : sel5 ? h[5] : h[6];
+            int32_t d[T];
+            int32_t sum = den_half;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                d[t] = top - h[t];
+                if (t >= 4) d[t] &= (int32_t)tmask[t];  // orders start at 4: taps 0..3 always live
+                sum -= c[t] * d[t];
+            }
+            const int32_t fir = sext_go(r + top + (sum >> den), cs);
+            const int32_t warm = (i == 0 || copy) ? r : sext_go(r + h[0], cs);
+            const bool is_fir = i >= fir_from;
+            const int32_t x = is_fir ? fir : warm;
+            // sign-LMS adaptation on the residual's sign: walk the taps from the oldest sample, stop once the
+            // running residual has changed sign or reached zero (predictor.go:137-185)
+            bool alive = is_fir && (r != 0);
+            const int32_t smask = r >> 31;           // 0 / -1
+            const int32_t sone = smask | 1;          // +1 / -1
+            const int32_t thr = 1 + smask;           // continue while (D ^ smask) >= thr <=> D > 0 (r>0) / D < 0 (r<0)
+            int32_t D = r;
+#pragma unroll
+            for (int t = T - 1; t >= 0; t--) {
+                const int32_t sg = max(min(d[t], 1), -1);  // signOfInt
+                const int32_t sgn = sg * sone;             // sign for r > 0, -sign for r < 0
+                if (alive) c[t] -= sgn;
+                if (t > 0) {
+                    const int32_t term = (sgn * d[t]) >> den;
+                    D -= wgt[t] * term;
+                    alive = alive && ((D ^ smask) >= thr);  // masked taps: term 0, D still r: stays alive
+                }
+            }
+#pragma unroll
+            for (int t = T; t > 0; t--) h[t] = h[t - 1];
+            h[0] = x;
+            if (i < n_lane) *outp = x;
+            outp += 32;
         }
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
@@ -807,7 +910,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 // Any mix of orders in the warp, including the int16-wrapping ones: unpcBlockGeneral, predictor.go:623-684,
 // with per-lane coefficient width (int32 kept for 4/5/6/8 as the reference's specialised loops do).
 __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
-                                            const Job &jb, bool active, int32_t *__restrict__ dst) {
+                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
@@ -826,7 +929,11 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
 #pragma unroll 1
     for (uint32_t ck = 0; ck < nchunks; ck++) {
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
-        if (ck > 0) mbar_wait(&sm.full_bar[cons][slot], par);
+        if (ck > 0) {
+            const unsigned long long tw = rt.now();
+            mbar_wait(&sm.full_bar[cons][slot], par);
+            rt.add(1, tw);
+        }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
 #pragma unroll 1
         for (uint32_t j = 0; j < CHUNK; j++) {
@@ -876,17 +983,21 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     int32_t *scratch_lane = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u + lane;
     uint32_t seq = 0;
+    RoleTimer rt(lane, 3 + 2 * cons);
+    const unsigned long long t_start = rt.now();
 #pragma unroll 1
     for (;;) {
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        const unsigned long long tw = rt.now();
         mbar_wait(&sm.full_bar[cons][slot], par);
+        rt.add(1, tw);
         Job jb;
         jb.n = sm.job[cons][slot][0][lane];
         const uint32_t meta = sm.job[cons][slot][1][lane];
         jb.coef_bitpos = sm.job[cons][slot][2][lane];
         jb.nmax = sm.job[cons][slot][3][lane];
         jb.kind = meta & 3u;
-        if (jb.kind == JOB_EXIT) break;  // written for every lane
+        if (jb.kind == JOB_EXIT) break;  // written for every lane (the wait for it is idle time, not work)
         jb.order = (meta >> 2) & 31u;
         jb.den = (meta >> 7) & 15u;
         jb.mode = (meta >> 11) & 1u;
@@ -897,14 +1008,20 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
         int32_t *dst = scratch_lane + (size_t)jb.slot * cfg.frame_length * 32u;
         const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
         const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
-        if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst);
-        else if (any8) stream_reg<8>(sm, lane, cons, seq, pk, jb, active, dst);
-        else stream_reg<6>(sm, lane, cons, seq, pk, jb, active, dst);
+        const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
+        if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt);
+        else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
+            if (any8) stream_reg<8, true>(sm, lane, cons, seq, pk, jb, active, dst, rt);
+            else stream_reg<6, true>(sm, lane, cons, seq, pk, jb, active, dst, rt);
+        } else if (any8) stream_reg<8, false>(sm, lane, cons, seq, pk, jb, active, dst, rt);
+        else stream_reg<6, false>(sm, lane, cons, seq, pk, jb, active, dst, rt);
     }
+    rt.add(0, t_start);
+    rt.flush(2);
 }
 
 // decodePacketInto for 32 packets per CTA, decoder.go:133-207.
-__global__ void __launch_bounds__(DEC_THREADS) alac_decode_kernel(const uint8_t *__restrict__ packed,
+__global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8_t *__restrict__ packed,
                                                                   const uint64_t *__restrict__ offsets,
                                                                   const uint32_t *__restrict__ sizes, uint32_t npackets,
                                                                   DevConfig cfg, int32_t *__restrict__ scratch,
