@@ -410,7 +410,7 @@ __constant__ int8_t k_layout[8][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 
 // ====================================================================================================
 constexpr uint32_t FULL_MASK = 0xffffffffu;
 
-enum : uint32_t { BUSY_ZERO_RUN = 1, BUSY_ESCAPE = 2, BUSY_LONG_CODES = 4, BUSY_DEAD = 8 };
+enum : uint32_t { BUSY_ESCAPE = 2, BUSY_LONG_CODES = 4, BUSY_DEAD = 8 };
 
 // What one lane needs to produce one stream (a channel of a compressed element, or the raw samples of an
 // escape element).
@@ -509,24 +509,48 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                     if (r > 0xffffu) mean2 = 0xffffu;
                     e.mean = mean2;
                     e.zmode = 0;
-                    // the zero-run code that follows (golomb.go:220) is read by the general step of the next sample
-                    busy |= zero_run_due(mean2, i, sp.n) ? BUSY_ZERO_RUN : 0u;
+                    if (zero_run_due(mean2, i, sp.n)) {
+                        // the run-length code that follows (dynGet, golomb.go:112-144, :220-245), straight-line
+                        int32_t k32 = __clz((int32_t)mean2) - 24 + (int32_t)((mean2 + 16u) >> 6);
+                        k32 = max(k32, 0);
+                        if (k32 > 16 || (bp >> 3) > pk.size) {  // never for a sane mean / position: general code
+                            if (!zero_run_start(pk, br, bp, e, i, sp.n, st)) {
+                                active = false;
+                                busy |= BUSY_DEAD;
+                            }
+                        } else {
+                            const uint32_t nxt2 = br.load(br.qn);  // the word after lo, should the first code have refilled
+                            const uint32_t mz = ((1u << k32) - 1u) & e.wb;
+                            const uint32_t w2 = br.window();
+                            const uint32_t pre2 = clz_nz(~w2);
+                            const bool esc2 = pre2 >= 9u;
+                            const uint32_t val = shr_go(w2 << ((pre2 + 1u) & 31u), 32u - (uint32_t)k32);
+                            const bool big2 = val >= 2u;
+                            const uint32_t run = esc2 ? ((w2 << 9) >> 16) : pre2 * mz + (big2 ? val - 1u : 0u);
+                            const uint32_t nb2 = esc2 ? 25u : pre2 + (uint32_t)k32 + (big2 ? 1u : 0u);
+                            br.nxt = nxt2;
+                            br.commit(br.sh + nb2);  // nb2 <= 26: one refill at most
+                            bp += nb2;
+                            if (i + 1u + run > sp.n) {  // golomb.go:232-234
+                                st = ST_SAMPLE_OVERRUN;
+                                active = false;
+                                busy |= BUSY_DEAD;
+                            }
+                            e.zrun = run;
+                            e.zmode = run >= 65535u ? 0u : 1u;
+                            e.mean = 0;
+                        }
+                    }
                 } else if (j < cnt && !(busy & BUSY_DEAD)) {
-                    if (sp.escape) {
+                    if (e.zrun > 0u && busy == 0u) {  // inside a zero run (clear(predCoefs[count:end]), golomb.go:237)
+                        e.zrun--;
+                    } else if (sp.escape) {
                         res = escape_sample(br, sp.chan_bits);
                         if (pair) res2 = escape_sample(br, sp.chan_bits);
-                    } else {
-                        bool ok = true;
-                        if (busy & BUSY_ZERO_RUN) {
-                            busy &= ~BUSY_ZERO_RUN;
-                            ok = zero_run_start(pk, br, bp, e, i - 1u, sp.n, st);
-                        }
-                        if (ok) ok = entropy_next(pk, br, bp, e, i, sp.n, res, st);
-                        if (!ok) {
-                            active = false;
-                            busy |= BUSY_DEAD;  // a failed lane idles through the rest of the stream
-                            res = 0;
-                        }
+                    } else if (!entropy_next(pk, br, bp, e, i, sp.n, res, st)) {
+                        active = false;
+                        busy |= BUSY_DEAD;  // a failed lane idles through the rest of the stream
+                        res = 0;
                     }
                 }
                 dst[j * 32] = res;
