@@ -30,7 +30,7 @@ bool cuda_ok(cudaError_t e, const char *what) {
         if (!cuda_ok((call), #call)) return ALACB200_E_CUDA; \
     } while (0)
 
-constexpr int kSlots = 3;  // pipeline depth of the host-buffer path
+constexpr int kSlots = 4;  // pipeline depth of the host-buffer path
 
 struct DevBuf {
     void *p = nullptr;
@@ -90,8 +90,14 @@ struct Slot {
     cudaStream_t stream = nullptr;
     Work work;
     DevBuf packed, offsets, sizes, pcm, out_bytes, status;
-    PinBuf h_offsets;  // rebased offsets staged for the H2D copy
+    PinBuf h_in;   // pinned staging of this chunk's rebased offsets (u64) + sizes (u32)
+    PinBuf h_out;  // pinned staging of this chunk's out_bytes (u32) + status (i32)
     cudaEvent_t done = nullptr;
+    // where h_out goes once the chunk has finished (caller arrays may be pageable: copying into them straight
+    // from the stream would make every chunk synchronous)
+    uint32_t *user_out_bytes = nullptr;
+    int32_t *user_status = nullptr;
+    uint32_t pending = 0;
 };
 
 struct ProfEvents {
@@ -311,7 +317,8 @@ void alacb200_destroy(alacb200_decoder *dec) {
         s.pcm.release();
         s.out_bytes.release();
         s.status.release();
-        s.h_offsets.release();
+        s.h_in.release();
+        s.h_out.release();
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -367,7 +374,7 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
     if (!guard.ok) return ALACB200_E_CUDA;
 
     // Chunk the batch so copies of chunk k+1 / k-1 overlap the kernels of chunk k.
-    uint32_t chunk = (n + 3u) / 4u;
+    uint32_t chunk = (n + 5u) / 6u;
     chunk = std::min(std::max(chunk, 1024u), 8192u);
     const uint64_t max_chunk_pcm = 512ull << 20;
     while (chunk > 32u && (uint64_t)chunk * out_stride > max_chunk_pcm) chunk /= 2u;
@@ -375,10 +382,20 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
 
     int32_t rc = ALACB200_OK;
     uint32_t slot_idx = 0;
+    auto retire = [](Slot &s) -> bool {  // wait for the slot's chunk and hand its per-packet results to the caller
+        if (cudaEventSynchronize(s.done) != cudaSuccess) return false;
+        if (s.pending) {
+            const uint32_t *ob = (const uint32_t *)s.h_out.p;
+            std::memcpy(s.user_out_bytes, ob, (size_t)s.pending * 4);
+            std::memcpy(s.user_status, ob + s.pending, (size_t)s.pending * 4);
+            s.pending = 0;
+        }
+        return true;
+    };
     for (uint32_t a = 0; a < n && rc == ALACB200_OK; a += chunk, slot_idx = (slot_idx + 1) % kSlots) {
         const uint32_t b = std::min(n, a + chunk), m = b - a;
         Slot &s = dec->slots[slot_idx];
-        CU(cudaEventSynchronize(s.done));  // the slot's previous chunk (and its staging) is finished
+        if (!retire(s)) return ALACB200_E_CUDA;  // the slot's previous chunk (and its staging) is finished
         // byte range of this chunk inside `packed`
         uint64_t lo = UINT64_MAX, hi = 0;
         for (uint32_t i = a; i < b; i++) {
@@ -389,29 +406,35 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
         const uint32_t mis = (uint32_t)(lo & 15u);  // keep each packet's alignment relative to 16 bytes
         const uint64_t span = hi - lo;
         if (!s.packed.reserve(mis + span + 64) || !s.offsets.reserve((size_t)m * 8) || !s.sizes.reserve((size_t)m * 4) ||
-            !s.out_bytes.reserve((size_t)m * 4) || !s.status.reserve((size_t)m * 4) ||
-            !s.h_offsets.reserve((size_t)m * 8))
+            !s.out_bytes.reserve((size_t)m * 8) || !s.h_in.reserve((size_t)m * 12) || !s.h_out.reserve((size_t)m * 8))
             return ALACB200_E_NOMEM;
         if ((size_t)m * out_stride > s.pcm.cap) {
             if (!s.pcm.reserve((size_t)m * out_stride)) return ALACB200_E_NOMEM;
             // the kernels never touch the gap between frame_bytes and out_stride: define it once
             CU(cudaMemsetAsync(s.pcm.p, 0, s.pcm.cap, s.stream));
         }
-        uint64_t *ho = (uint64_t *)s.h_offsets.p;
+        uint64_t *ho = (uint64_t *)s.h_in.p;
+        uint32_t *hs = (uint32_t *)(ho + m);
         for (uint32_t i = 0; i < m; i++) ho[i] = offsets[a + i] - lo + mis;
+        std::memcpy(hs, sizes + a, (size_t)m * 4);
+        uint32_t *d_ob = (uint32_t *)s.out_bytes.p;  // out_bytes[m] then status[m], one D2H copy
+        int32_t *d_st = (int32_t *)(d_ob + m);
         if (span) CU(cudaMemcpyAsync((uint8_t *)s.packed.p + mis, packed + lo, span, cudaMemcpyHostToDevice, s.stream));
         CU(cudaMemcpyAsync(s.offsets.p, ho, (size_t)m * 8, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.sizes.p, sizes + a, (size_t)m * 4, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.sizes.p, hs, (size_t)m * 4, cudaMemcpyHostToDevice, s.stream));
         rc = launch(dec, s.work, (const uint8_t *)s.packed.p, (const uint64_t *)s.offsets.p, (const uint32_t *)s.sizes.p, m,
-                    (uint8_t *)s.pcm.p, out_stride, (uint32_t *)s.out_bytes.p, (int32_t *)s.status.p, s.stream);
+                    (uint8_t *)s.pcm.p, out_stride, d_ob, d_st, s.stream);
         if (rc != ALACB200_OK) break;
         CU(cudaMemcpyAsync(pcm_out + (size_t)a * out_stride, s.pcm.p, (size_t)(m - 1) * out_stride + dec->frame_bytes,
                            cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(out_bytes + a, s.out_bytes.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(status + a, s.status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_out.p, d_ob, (size_t)m * 8, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.done, s.stream));
+        s.user_out_bytes = out_bytes + a;
+        s.user_status = status + a;
+        s.pending = m;
     }
-    for (auto &s : dec->slots) CU(cudaStreamSynchronize(s.stream));
+    for (auto &s : dec->slots)
+        if (!retire(s)) return ALACB200_E_CUDA;
     return rc;
 }
 
