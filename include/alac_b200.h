@@ -140,10 +140,10 @@ int32_t alacb200_device_count(void);
 
 /* Per-kernel device timing (CUDA events on the launch stream), for bench.py's roofline line. */
 typedef struct alacb200_profile {
-    uint64_t launches_decode;   /* alac_decode_kernel launches since enable */
-    uint64_t launches_emit;     /* alac_emit_kernel launches since enable */
-    double ms_decode;           /* summed event time of the decode kernel */
-    double ms_emit;             /* summed event time of the emit kernel */
+    uint64_t launches_decode;   /* alac_decode_kernel launches since enable (stages 1-3 are one kernel) */
+    uint64_t launches_emit;     /* reserved: 0 (stage 3 runs as the tail of alac_decode_kernel) */
+    double ms_decode;           /* summed event time of alac_decode_kernel */
+    double ms_emit;             /* reserved: 0 */
 } alacb200_profile;
 int32_t alacb200_set_profiling(alacb200_decoder *dec, int enable); /* enabling resets the counters */
 int32_t alacb200_get_profile(alacb200_decoder *dec, alacb200_profile *out); /* synchronises the recorded events */

@@ -101,7 +101,7 @@ struct Slot {
 };
 
 struct ProfEvents {
-    cudaEvent_t e0, e1, e2;
+    cudaEvent_t e0, e1;
 };
 
 }  // namespace
@@ -139,11 +139,6 @@ int32_t check_config(const alacb200_config *cfg) {
     return ALACB200_ST_OK;
 }
 
-size_t emit_smem_bytes(const DevConfig &c) {
-    uint32_t fb = c.num_channels * c.bps;
-    uint32_t row_words = (EMIT_TILE * fb) / 4u + 1u;
-    return (size_t)row_words * 4u * 32u;
-}
 
 // Enqueue decode + emit for n device-resident packets on `stream`.
 int32_t launch(alacb200_decoder *dec, Work &work, const uint8_t *d_packed, const uint64_t *d_offsets,
@@ -163,38 +158,29 @@ int32_t launch(alacb200_decoder *dec, Work &work, const uint8_t *d_packed, const
     if (dec->profiling) {
         CU(cudaEventCreate(&pe.e0));
         CU(cudaEventCreate(&pe.e1));
-        CU(cudaEventCreate(&pe.e2));
         CU(cudaEventRecord(pe.e0, stream));
     }
-    alac_decode_kernel<<<groups, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
-                                                  (PacketDesc *)work.descs.p, d_out_bytes, d_status);
-    CU(cudaGetLastError());
-    if (dec->profiling) CU(cudaEventRecord(pe.e1, stream));
-    const uint32_t tiles = (c.frame_length + EMIT_TILE - 1) / EMIT_TILE;
-    alac_emit_kernel<<<groups * tiles, EMIT_THREADS, emit_smem_bytes(c), stream>>>(
-        d_packed, d_offsets, d_sizes, n, c, (const int32_t *)work.scratch.p, (const PacketDesc *)work.descs.p, d_pcm,
-        out_stride, tiles);
+    alac_decode_kernel<<<groups, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c,
+                                                                           (int32_t *)work.scratch.p,
+                                                                           (PacketDesc *)work.descs.p, d_pcm, out_stride,
+                                                                           d_out_bytes, d_status);
     CU(cudaGetLastError());
     if (dec->profiling) {
-        CU(cudaEventRecord(pe.e2, stream));
+        CU(cudaEventRecord(pe.e1, stream));
         dec->prof_events.push_back(pe);
         dec->prof.launches_decode++;
-        dec->prof.launches_emit++;
     }
     return ALACB200_OK;
 }
 
 int32_t drain_profile(alacb200_decoder *dec) {
     for (auto &pe : dec->prof_events) {
-        CU(cudaEventSynchronize(pe.e2));
-        float a = 0, b = 0;
+        CU(cudaEventSynchronize(pe.e1));
+        float a = 0;
         CU(cudaEventElapsedTime(&a, pe.e0, pe.e1));
-        CU(cudaEventElapsedTime(&b, pe.e1, pe.e2));
         dec->prof.ms_decode += a;
-        dec->prof.ms_emit += b;
         cudaEventDestroy(pe.e0);
         cudaEventDestroy(pe.e1);
-        cudaEventDestroy(pe.e2);
     }
     dec->prof_events.clear();
     return ALACB200_OK;
@@ -275,13 +261,7 @@ int32_t alacb200_create(const alacb200_config *cfg, int device, alacb200_decoder
     dec->dev_cfg.mb = cfg->mb;
     dec->dev_cfg.kb = cfg->kb;
     dec->frame_bytes = (uint64_t)cfg->frame_length * cfg->num_channels * dec->dev_cfg.bps;
-    cudaError_t e = cudaFuncSetAttribute(alac_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)emit_smem_bytes(dec->dev_cfg));
-    if (!cuda_ok(e, "cudaFuncSetAttribute(alac_emit_kernel)")) {
-        delete dec;
-        return ALACB200_E_CUDA;
-    }
-    e = cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
+    cudaError_t e = cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
     if (!cuda_ok(e, "cudaFuncSetAttribute(alac_decode_kernel)")) {
         delete dec;
         return ALACB200_E_CUDA;
@@ -304,7 +284,6 @@ void alacb200_destroy(alacb200_decoder *dec) {
     for (auto &pe : dec->prof_events) {
         cudaEventDestroy(pe.e0);
         cudaEventDestroy(pe.e1);
-        cudaEventDestroy(pe.e2);
     }
     dec->device_path_work.scratch.release();
     dec->device_path_work.descs.release();

@@ -22,6 +22,7 @@
 // coefficients otherwise (predictor.go:107-110 vs :664). Where the reference would panic the packet
 // gets ST_REF_PANIC.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -150,7 +151,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
-// Optional role timing (clock64 per role, lane 0): [cta][8] = E total, E wait-empty, E top-up, P0 total, P0 wait,
+// Optional role timing (clock64 per role, lane 0): [cta][16] (8..10 = emit tail per warp), E total, E wait-empty, E top-up, P0 total, P0 wait,
 // P1 total, P1 wait, unused. Enabled by pointing g_role_cycles at a buffer (alacb200_debug_role_cycles).
 __device__ unsigned long long *g_role_cycles = nullptr;
 struct RoleTimer {
@@ -158,7 +159,7 @@ struct RoleTimer {
     unsigned long long acc[3] = {0, 0, 0};
     __device__ __forceinline__ RoleTimer(uint32_t lane, int base) {
         unsigned long long *b = g_role_cycles;
-        slot = (b != nullptr && lane == 0) ? b + (size_t)blockIdx.x * 8 + base : nullptr;
+        slot = (b != nullptr && lane == 0) ? b + (size_t)blockIdx.x * 16 + base : nullptr;
     }
     __device__ __forceinline__ unsigned long long now() const { return slot ? clock64() : 0ull; }
     __device__ __forceinline__ void add(int k, unsigned long long t0) { if (slot) acc[k] += clock64() - t0; }
@@ -1044,14 +1045,428 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
     rt.flush(2);
 }
 
-// decodePacketInto for 32 packets per CTA, decoder.go:133-207.
+// ---- stage 3 ---------------------------------------------------------------------------------------
+// WriteStereo16/20/24/32 + WriteMono16/20/24/32 (matrix.go:30-301) for the 32 packets of one group, run by
+// the whole CTA once its role warps are done. Lane = packet reads the parked samples coalesced, un-mixes,
+// merges the shift bytes, writes the little-endian bytes into a shared-memory tile (odd word stride:
+// conflict-free transpose); then each warp flushes packet rows with 128-bit stores. The element ops are
+// replayed in element order with a barrier in between, so later elements overwrite earlier ones exactly as
+// the sequential reference does (a pair mapped onto the last channel spills into the next frame,
+// matrix.go:44-48). Bytes past output[:n] (decoder.go:127) and failed packets are written as zeros.
+struct EmitArgs {
+    const uint8_t *packed;
+    const uint64_t *offsets;
+    const uint32_t *sizes;
+    uint32_t npackets;
+    const int32_t *scratch;
+    const PacketDesc *descs;
+    uint8_t *pcm_out;
+    uint64_t out_stride;
+};
+
+__device__ __forceinline__ void tile_put(uint8_t *row, int32_t lo_byte, int32_t hi_byte, int32_t off, int32_t v, int bps) {
+    // store the bps little-endian bytes of v at packet byte offset `off`, clipped to the tile [lo_byte, hi_byte)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < bps) {
+            int32_t o = off + k;
+            if (o >= lo_byte && o < hi_byte) row[o - lo_byte] = (uint8_t)((uint32_t)v >> (8 * k));
+        }
+    }
+}
+
+// sb (8 or 16) bits at bit offset `rel` of a staged shift row (bytes in stream order, 32-bit words as loaded)
+__device__ __forceinline__ uint32_t shift_field(const uint32_t *row_words, uint32_t rel, uint32_t sb) {
+    const uint32_t b = rel >> 3;
+    const uint32_t w0 = __byte_perm(row_words[b >> 2], 0, 0x0123);
+    const uint32_t w1 = __byte_perm(row_words[(b >> 2) + 1u], 0, 0x0123);
+    const uint32_t win = __funnelshift_l(w1, w0, (b & 3u) * 8u + (rel & 7u));  // < 32
+    return win >> (32u - sb);
+}
+
+// the little-endian bytes of one mono sample / one stereo pair into the transpose tile, widest aligned stores
+template <int BPS>
+__device__ __forceinline__ void tile_store(uint8_t *dst, int32_t left, int32_t right, bool stereo) {
+    const uint64_t lmask = BPS == 4 ? 0xffffffffull : ((1ull << (8 * BPS)) - 1ull);
+    uint64_t v = (uint64_t)(uint32_t)left & lmask;
+    if (stereo) v |= ((uint64_t)(uint32_t)right & lmask) << (8 * BPS);
+    const uint32_t nbytes = stereo ? 2u * BPS : (uint32_t)BPS;
+    const uint32_t a = (uint32_t)(uintptr_t)dst;
+    if ((a & 3u) == 0 && nbytes == 4u) {
+        *reinterpret_cast<uint32_t *>(dst) = (uint32_t)v;
+    } else if ((a & 3u) == 0 && nbytes == 8u) {
+        *reinterpret_cast<uint32_t *>(dst) = (uint32_t)v;
+        *reinterpret_cast<uint32_t *>(dst + 4) = (uint32_t)(v >> 32);
+    } else if ((a & 1u) == 0 && (nbytes & 1u) == 0) {
+#pragma unroll
+        for (int k = 0; k < BPS; k++)
+            if (2u * (uint32_t)k < nbytes) *reinterpret_cast<uint16_t *>(dst + 2 * k) = (uint16_t)(v >> (16 * k));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2 * BPS; k++)
+            if ((uint32_t)k < nbytes) dst[k] = (uint8_t)(v >> (8 * k));
+    }
+}
+
+struct EmitOp {
+    const int32_t *su, *sv;
+    int32_t i_lo, i_hi, s0, mix_res;
+    uint32_t mix_bits, sb, rel0, width, fb, out_off;
+    bool stereo, depth20;
+};
+
+// frames [i_lo, i_hi) of one element, all inside the tile: batched parked-sample loads, un-mix, shift merge, store
+template <int BPS>
+__device__ __forceinline__ void emit_frames(const EmitOp &o, uint8_t *row, const uint32_t *shrow_words) {
+    constexpr int EB = 8;  // frames per batch: all parked-sample loads of a batch are issued together
+#pragma unroll 1
+    for (int32_t ib = o.i_lo; ib < o.i_hi; ib += EB) {
+        int32_t lu[EB], lv[EB];
+#pragma unroll
+        for (int q = 0; q < EB; q++) {
+            const int32_t i = min(ib + q, o.i_hi - 1);
+            lu[q] = __ldcs(o.su + (size_t)i * 32u);  // parked samples are read exactly once
+            lv[q] = __ldcs(o.sv + (size_t)i * 32u);
+        }
+#pragma unroll
+        for (int q = 0; q < EB; q++) {
+            const int32_t i = ib + q;
+            if (i < o.i_hi) {
+                int32_t left = lu[q], right = o.stereo ? lv[q] : 0;
+                if (o.stereo && o.mix_res != 0) {  // matrix.go:40-41
+                    const int32_t v = right;
+                    left = left + v - sar_go(o.mix_res * v, o.mix_bits);
+                    right = left - v;
+                }
+                if (o.depth20) {
+                    left = (int32_t)((uint32_t)left << 4);
+                    right = (int32_t)((uint32_t)right << 4);
+                }
+                if (o.sb) {  // shift buffer merge, matrix.go:132-135, :270-272 (BitBuffer.Read of sb bits)
+                    const uint32_t rel = o.rel0 + (uint32_t)(i - o.i_lo) * o.width * o.sb;
+                    left = (int32_t)shl_go((uint32_t)left, o.sb) | (int32_t)shift_field(shrow_words, rel, o.sb);
+                    if (o.stereo) right = (int32_t)shl_go((uint32_t)right, o.sb) | (int32_t)shift_field(shrow_words, rel + o.sb, o.sb);
+                }
+                tile_store<BPS>(row + (uint32_t)(i - o.s0) * o.fb + o.out_off, left, right, o.stereo);
+            }
+        }
+    }
+}
+
+// ---- stage 3, direct path: the element covers the whole frame (mono in a 1-channel stream, a pair in a
+// 2-channel stream). Each lane then owns contiguous output: 16 frames are un-mixed, shift-merged and packed into
+// registers and leave as FB 128-bit stores to the lane's own packet slot -- no transpose tile, no barrier. All
+// parked-sample and shift-word loads of a batch are issued together (32 + ~10 per lane) so that nine warps per SM
+// keep enough bytes in flight. Frames past the element's sample count are written as zeros (decoder.go:120, :127).
+template <int BPS, int WIDTH>
+__device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
+                                            bool valid, const Packet &pk, const OpDesc &op, uint32_t n_final) {
+    constexpr int FB = BPS * WIDTH;  // bytes per frame
+    constexpr int EB = 16;           // frames per batch: 16*FB bytes = FB 128-bit stores
+    constexpr uint32_t SROW = 21;    // shift words staged per lane and batch: 16 frames x 2 x 2 bytes + window + slack, odd
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    constexpr uint32_t NW = DEC_THREADS / 32;
+    uint32_t *myrow = reinterpret_cast<uint32_t *>(smem) + ((size_t)warp * 32u + lane) * SROW;
+    const uint32_t pidx = group * 32u + lane;
+    const bool stereo = WIDTH == 2;
+    const bool depth20 = cfg.bit_depth == 20;
+    const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;
+    const uint32_t sb = (merges_shift ? (uint32_t)op.shift : 0u) * 8u;
+    const uint32_t n_op = min(op.n, n_final);  // output[:n] cuts what an earlier, longer element wrote
+    const int32_t *su = x.scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+    const int32_t *sv = stereo ? su + (size_t)cfg.frame_length * 32u : su;
+    uint8_t *slot = x.pcm_out + (size_t)pidx * x.out_stride;
+    const bool vec_ok = ((((uintptr_t)x.pcm_out) | x.out_stride) & 15u) == 0;
+    const uint32_t nbatches = (cfg.frame_length + EB - 1) / EB;
+    const int32_t mix_res = op.mix_res;
+    const uint32_t mix_bits = op.mix_bits;
+#pragma unroll 1
+    for (uint32_t b = warp; b < nbatches; b += NW) {
+        const uint32_t f0 = b * EB;
+        const uint32_t cnt = n_op > f0 ? min((uint32_t)EB, n_op - f0) : 0u;
+        // ---- issue every load of the batch -----------------------------------------------------------------
+        int32_t lu[EB], lv[EB];
+        const uint32_t last = n_op > 0 ? n_op - 1u : 0u;
+#pragma unroll
+        for (int q = 0; q < EB; q++) {
+            const uint32_t i = min(f0 + (uint32_t)q, last);
+            lu[q] = __ldcs(su + (size_t)i * 32u);
+            lv[q] = __ldcs(sv + (size_t)i * 32u);
+        }
+        uint32_t rel0 = 0;
+        if (sb && cnt) {
+            const uint32_t first_bit = op.shift_bitpos + f0 * WIDTH * sb;
+            const uint32_t nbits = cnt * WIDTH * sb;
+            const uint32_t byte0 = first_bit >> 3;
+            const uint32_t nbytes = ((first_bit & 7u) + nbits + 7u) / 8u + 2u;  // +2: the 24-bit window of BitBuffer.Read
+            const uintptr_t ga = ((uintptr_t)(pk.p + byte0)) & ~(uintptr_t)3;
+            const uint32_t lead_bytes = (uint32_t)((uintptr_t)(pk.p + byte0) - ga);
+            const int64_t rel_pk = (int64_t)byte0 - (int64_t)lead_bytes;
+            const uint32_t nw = (lead_bytes + nbytes + 3u) / 4u;  // <= 18
+            const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(ga);
+            uint32_t wbuf[SROW - 2];
+#pragma unroll
+            for (uint32_t k = 0; k < SROW - 2; k++) {
+                const int64_t b_first = rel_pk + 4 * (int64_t)k;
+                uint32_t w = 0;
+                if (k < nw) {
+                    if (b_first + 4 <= (int64_t)pk.size) w = __ldg(gsrc + k);
+                    else {  // bytes at or past the packet end read as zero (bitbuffer.go:36-51)
+                        for (int j = 0; j < 4; j++)
+                            if (b_first + j >= 0 && b_first + j < (int64_t)pk.size) w |= (uint32_t)__ldg(pk.p + (b_first + j)) << (8 * j);
+                    }
+                }
+                wbuf[k] = w;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < SROW - 2; k++) myrow[k] = wbuf[k];
+            myrow[SROW - 2] = 0;
+            myrow[SROW - 1] = 0;
+            rel0 = lead_bytes * 8u + (first_bit & 7u);
+        }
+        // ---- un-mix, merge, pack ------------------------------------------------------------------------------
+        uint32_t ow[4 * FB];
+#pragma unroll
+        for (int k = 0; k < 4 * FB; k++) ow[k] = 0;
+#pragma unroll
+        for (int q = 0; q < EB; q++) {
+            int32_t left = lu[q], right = stereo ? lv[q] : 0;
+            if (stereo && mix_res != 0) {  // matrix.go:40-41
+                const int32_t v = right;
+                left = left + v - sar_go(mix_res * v, mix_bits);
+                right = left - v;
+            }
+            if (depth20) {
+                left = (int32_t)((uint32_t)left << 4);
+                right = (int32_t)((uint32_t)right << 4);
+            }
+            if (sb) {  // shift buffer merge, matrix.go:132-135, :270-272
+                const uint32_t rel = rel0 + (uint32_t)q * WIDTH * sb;
+                left = (int32_t)shl_go((uint32_t)left, sb) | (int32_t)shift_field(myrow, rel, sb);
+                if (stereo) right = (int32_t)shl_go((uint32_t)right, sb) | (int32_t)shift_field(myrow, rel + sb, sb);
+            }
+            constexpr uint64_t lmask = BPS == 4 ? 0xffffffffull : ((1ull << (8 * BPS)) - 1ull);
+            uint64_t v = (uint64_t)(uint32_t)left & lmask;
+            if (stereo) v |= ((uint64_t)(uint32_t)right & lmask) << (8 * BPS);
+            if ((uint32_t)q >= cnt) v = 0;  // frames past the sample count stay zero
+            const int bit = q * FB * 8;  // static after unrolling
+            const int wi = bit / 32, sh = bit % 32;
+            ow[wi] |= (uint32_t)(v << sh);
+            if (sh + FB * 8 > 32) ow[wi + 1] |= (uint32_t)(v >> (32 - sh));
+            if (sh + FB * 8 > 64) ow[wi + 2] |= (uint32_t)(v >> (64 - sh));
+        }
+        // ---- store: FB x 16 bytes to the lane's own packet slot ---------------------------------------------------
+        if (valid) {
+            uint8_t *dst = slot + (size_t)f0 * FB;
+            const uint32_t frames_here = min((uint32_t)EB, cfg.frame_length - f0);
+            if (frames_here == EB && vec_ok) {
+#pragma unroll
+                for (int k = 0; k < FB; k++)
+                    reinterpret_cast<uint4 *>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+            } else {  // last, short batch of an odd frame length, or a slot that is only 4-byte aligned
+                const uint32_t nb = frames_here * FB;
+#pragma unroll
+                for (int k = 0; k < 4 * FB; k++) {
+                    if ((uint32_t)(4 * k + 4) <= nb) reinterpret_cast<uint32_t *>(dst)[k] = ow[k];
+                    else
+                        for (int j = 0; j < 4; j++)
+                            if ((uint32_t)(4 * k + j) < nb) dst[4 * k + j] = (uint8_t)(ow[k] >> (8 * j));
+                }
+            }
+        }
+    }
+}
+
+// Stage 3 runs warp-local: every warp owns a transpose tile of 32 packet rows x TL frames (+ a staging row for
+// the shift bytes) inside the shared memory the decode stage leaves behind, and walks the tiles w, w+NWARPS, ...
+// of the group on its own -- no block barrier, three tiles in flight per CTA.
+__host__ __device__ inline uint32_t emit_tile_frames(uint32_t frame_bytes, uint32_t nwarps, uint32_t smem_bytes) {
+    // per packet row: TL*fb + 4 bytes of tile (odd word stride) and 4*TL + 12 bytes of shift staging
+    // (TL frames x 2 channels x 2 shift bytes, + the 24-bit window of BitBuffer.Read, odd word stride)
+    const uint32_t per_row = smem_bytes / (nwarps * 32u);
+    uint32_t tl = (per_row - 28u) / (frame_bytes + 4u);
+    tl = tl > 64u ? 64u : tl;
+    return tl >= 16u ? (tl & ~15u) : (tl & ~3u);  // keep TL*fb a multiple of 16 where possible (128-bit stores)
+}
+
+template <int NWARPS>
+__device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
+                                           uint32_t smem_bytes) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t fb = cfg.num_channels * cfg.bps;  // bytes per frame
+    const uint32_t TL = emit_tile_frames(fb, NWARPS, smem_bytes);
+    const uint32_t row_words = (TL * fb) / 4u + 1u;  // odd => conflict-free lane-per-row access
+    const uint32_t EMIT_SHIFT_ROW_WORDS = TL + 5u;   // TL is a multiple of 4: odd; +2 words so a 64-bit window never runs off
+    const uint32_t warp_words = 32u * (row_words + EMIT_SHIFT_ROW_WORDS);
+    uint32_t *sw = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * warp_words;  // this warp's tile
+    uint32_t *shw = sw + 32u * row_words;                                             // this warp's shift rows
+    const uint32_t pidx = group * 32u + lane;
+    const bool valid = pidx < x.npackets;
+    const PacketDesc *desc = x.descs + pidx;
+    int32_t st = ST_REF_PANIC;
+    uint32_t nops = 0, n_final = 0;
+    Packet pk{x.packed, 0};
+    if (valid) {
+        st = desc->status;
+        nops = st == ST_OK ? desc->nops : 0;
+        n_final = st == ST_OK ? desc->n_final : 0;
+        pk = Packet{x.packed + x.offsets[pidx], x.sizes[pidx]};
+    }
+    const uint32_t max_ops = __reduce_max_sync(FULL_MASK, nops);
+    // direct path when, for every packet of the group, one element covers the whole frame (or nothing is written)
+    {
+        OpDesc op0;
+        op0.n = 0; op0.shift_bitpos = 0; op0.kind = 0; op0.out_chan = 0; op0.slot = 0; op0.shift = 0; op0.mix_bits = 0; op0.mix_res = 0;
+        if (nops == 1) op0 = desc->ops[0];
+        const bool whole = cfg.num_channels <= 2u && (nops == 0 || (nops == 1 && op0.kind == cfg.num_channels && op0.out_chan == 0));
+        if (__all_sync(FULL_MASK, whole)) {
+            if (cfg.num_channels == 2u) {
+                if (cfg.bps == 3) emit_direct<3, 2>(x, cfg, group, smem, valid, pk, op0, n_final);
+                else if (cfg.bps == 2) emit_direct<2, 2>(x, cfg, group, smem, valid, pk, op0, n_final);
+                else emit_direct<4, 2>(x, cfg, group, smem, valid, pk, op0, n_final);
+            } else {
+                if (cfg.bps == 3) emit_direct<3, 1>(x, cfg, group, smem, valid, pk, op0, n_final);
+                else if (cfg.bps == 2) emit_direct<2, 1>(x, cfg, group, smem, valid, pk, op0, n_final);
+                else emit_direct<4, 1>(x, cfg, group, smem, valid, pk, op0, n_final);
+            }
+            return;
+        }
+    }
+    uint8_t *row = reinterpret_cast<uint8_t *>(sw) + (size_t)lane * row_words * 4u;
+    const int32_t *sbase = x.scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+    const int bps = (int)cfg.bps;
+    const bool depth20 = cfg.bit_depth == 20;
+    const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;  // 16/20-bit writers ignore the shift buffer
+    const uint32_t ntiles = (cfg.frame_length + TL - 1u) / TL;
+
+#pragma unroll 1
+    for (uint32_t tile = warp; tile < ntiles; tile += NWARPS) {
+        const int32_t s0 = (int32_t)(tile * TL);
+        const int32_t lo_byte = s0 * (int32_t)fb, hi_byte = (s0 + (int32_t)TL) * (int32_t)fb;
+        __syncwarp();  // previous tile flushed
+        for (uint32_t i = lane; i < row_words * 32u; i += 32u) sw[i] = 0;  // fresh make(), decoder.go:120
+        __syncwarp();
+#pragma unroll 1
+        for (uint32_t e = 0; e < max_ops; e++) {
+            OpDesc op;
+            op.n = 0; op.shift_bitpos = 0; op.kind = 0; op.out_chan = 0; op.slot = 0; op.shift = 0; op.mix_bits = 0; op.mix_res = 0;
+            if (e < nops) op = desc->ops[e];
+            const bool stereo = op.kind == 2;
+            const uint32_t sb = (merges_shift ? (uint32_t)op.shift : 0u) * 8u;
+            // a pair mapped onto the last channel spills R into the next frame (matrix.go:44-48)
+            const bool spills = op.kind != 0 && (uint32_t)op.out_chan + (stereo ? 2u : 1u) > cfg.num_channels;
+            int32_t i_lo = spills ? s0 - 1 : s0;
+            i_lo = max(i_lo, 0);
+            const int32_t i_hi = min(s0 + (int32_t)TL, (int32_t)min(op.n, 0x7fffffffu));
+            // ---- stage the shift bytes of this lane's (op, tile) into its own shared row: 32-bit loads, 8 in flight ----
+            const uint32_t width = stereo ? 2u : 1u;
+            const uint32_t first_bit = op.shift_bitpos + (uint32_t)i_lo * width * sb;  // of frame i_lo
+            const uint32_t nbits = (i_hi > i_lo && sb) ? (uint32_t)(i_hi - i_lo) * width * sb : 0u;
+            uint32_t rel0 = 0;  // bit offset of frame i_lo's first field inside the staged row
+            if (nbits) {
+                const uint32_t byte0 = first_bit >> 3;
+                const uint32_t nbytes = ((first_bit & 7u) + nbits + 7u) / 8u + 2u;  // +2: the 24-bit window of BitBuffer.Read
+                const uintptr_t ga = ((uintptr_t)(pk.p + byte0)) & ~(uintptr_t)3;
+                const uint32_t lead_bytes = (uint32_t)((uintptr_t)(pk.p + byte0) - ga);
+                const int64_t rel_pk = (int64_t)byte0 - (int64_t)lead_bytes;  // packet byte index of staged byte 0
+                const uint32_t nw = (lead_bytes + nbytes + 3u) / 4u;           // <= TL + 3
+                uint32_t *myrow = shw + (size_t)lane * EMIT_SHIFT_ROW_WORDS;
+                const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(ga);
+#pragma unroll 8
+                for (uint32_t k = 0; k < nw; k++) {
+                    const int64_t b_first = rel_pk + 4 * (int64_t)k;
+                    uint32_t w = 0;
+                    if (b_first + 4 <= (int64_t)pk.size) w = __ldg(gsrc + k);
+                    else {  // bytes at or past the packet end read as zero (bitbuffer.go:36-51)
+                        for (int j = 0; j < 4; j++)
+                            if (b_first + j >= 0 && b_first + j < (int64_t)pk.size) w |= (uint32_t)__ldg(pk.p + (b_first + j)) << (8 * j);
+                    }
+                    myrow[k] = w;
+                }
+                myrow[nw] = 0;
+                myrow[nw + 1u] = 0;
+                rel0 = lead_bytes * 8u + (first_bit & 7u);
+            }
+            if (op.kind != 0) {
+                const int32_t *su = sbase + (size_t)op.slot * cfg.frame_length * 32u;
+                const int32_t *sv = stereo ? su + (size_t)cfg.frame_length * 32u : su;
+                if (!spills) {  // every byte of these frames lies inside the tile: no clipping
+                    EmitOp eo;
+                    eo.su = su; eo.sv = sv; eo.i_lo = i_lo; eo.i_hi = i_hi; eo.s0 = s0; eo.mix_res = op.mix_res;
+                    eo.mix_bits = op.mix_bits; eo.sb = sb; eo.rel0 = rel0; eo.width = width; eo.fb = fb;
+                    eo.out_off = (uint32_t)op.out_chan * cfg.bps; eo.stereo = stereo; eo.depth20 = depth20;
+                    const uint32_t *shrow_words = shw + (size_t)lane * EMIT_SHIFT_ROW_WORDS;
+                    if (bps == 3) emit_frames<3>(eo, row, shrow_words);
+                    else if (bps == 2) emit_frames<2>(eo, row, shrow_words);
+                    else emit_frames<4>(eo, row, shrow_words);
+                } else {  // a pair spilling over the frame end (non-canonical element order): clip byte by byte
+                    const int32_t mix_res = op.mix_res;
+                    const uint32_t mix_bits = op.mix_bits;
+#pragma unroll 1
+                    for (int32_t i = i_lo; i < i_hi; i++) {
+                        int32_t left = su[(size_t)i * 32u], right = stereo ? sv[(size_t)i * 32u] : 0;
+                        if (stereo && mix_res != 0) {  // matrix.go:40-41
+                            const int32_t v = right;
+                            left = left + v - sar_go(mix_res * v, mix_bits);
+                            right = left - v;
+                        }
+                        if (depth20) {
+                            left = (int32_t)((uint32_t)left << 4);
+                            right = (int32_t)((uint32_t)right << 4);
+                        }
+                        if (sb) {
+                            const uint32_t rel = rel0 + (uint32_t)(i - i_lo) * width * sb;
+                            const uint32_t *shrow_words = shw + (size_t)lane * EMIT_SHIFT_ROW_WORDS;
+                            left = (int32_t)shl_go((uint32_t)left, sb) | (int32_t)shift_field(shrow_words, rel, sb);
+                            if (stereo) right = (int32_t)shl_go((uint32_t)right, sb) | (int32_t)shift_field(shrow_words, rel + sb, sb);
+                        }
+                        const int32_t off = i * (int32_t)fb + (int32_t)op.out_chan * bps;
+                        tile_put(row, lo_byte, hi_byte, off, left, bps);
+                        if (stereo) tile_put(row, lo_byte, hi_byte, off + bps, right, bps);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // flush: the warp walks the 32 packet rows; the whole tile is written so the packet's slot is fully defined
+        const uint32_t tile_frames = min(TL, cfg.frame_length - (uint32_t)s0);
+        const uint32_t limit = tile_frames * fb;  // multiple of 4
+        for (uint32_t r = 0; r < 32u; r++) {
+            const uint32_t p = group * 32u + r;
+            if (p >= x.npackets) break;
+            const uint32_t r_nfinal = __shfl_sync(FULL_MASK, n_final, r);
+            int64_t nvalid = (int64_t)r_nfinal * fb - lo_byte;
+            nvalid = nvalid < 0 ? 0 : (nvalid > (int64_t)limit ? (int64_t)limit : nvalid);
+            uint32_t *src = sw + (size_t)r * row_words;
+            if ((uint32_t)nvalid < limit) {
+                uint8_t *srcb = reinterpret_cast<uint8_t *>(src);
+                for (uint32_t b2 = (uint32_t)nvalid + lane; b2 < limit; b2 += 32u) srcb[b2] = 0;
+                __syncwarp();
+            }
+            uint8_t *dst = x.pcm_out + (size_t)p * x.out_stride + (size_t)lo_byte;
+            const uint32_t nvec = limit >> 4;
+            if ((((uintptr_t)dst) & 15u) == 0) {
+                for (uint32_t v = lane; v < nvec; v += 32u) {
+                    uint4 q = make_uint4(src[v * 4u], src[v * 4u + 1u], src[v * 4u + 2u], src[v * 4u + 3u]);
+                    reinterpret_cast<uint4 *>(dst)[v] = q;
+                }
+            } else {
+                for (uint32_t w = lane; w < nvec * 4u; w += 32u) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
+            }
+            for (uint32_t w = nvec * 4u + lane; w < (limit >> 2); w += 32u) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
+        }
+    }
+}
+
+// decodePacketInto for 32 packets per CTA, decoder.go:133-207: role warps (stages 1+2), then the whole CTA emits.
 __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8_t *__restrict__ packed,
-                                                                  const uint64_t *__restrict__ offsets,
-                                                                  const uint32_t *__restrict__ sizes, uint32_t npackets,
-                                                                  DevConfig cfg, int32_t *__restrict__ scratch,
-                                                                  PacketDesc *__restrict__ descs,
-                                                                  uint32_t *__restrict__ out_bytes,
-                                                                  int32_t *__restrict__ status) {
+                                                                     const uint64_t *__restrict__ offsets,
+                                                                     const uint32_t *__restrict__ sizes, uint32_t npackets,
+                                                                     DevConfig cfg, int32_t *__restrict__ scratch,
+                                                                     PacketDesc *__restrict__ descs,
+                                                                     uint8_t *__restrict__ pcm_out, uint64_t out_stride,
+                                                                     uint32_t *__restrict__ out_bytes,
+                                                                     int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t dec_smem[];
     DecShared &sm = *reinterpret_cast<DecShared *>(dec_smem);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1067,140 +1482,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
     const uint32_t role = (warp + blockIdx.x) % 3u;
     if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
     else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch);
-}
-
-// ---- stage 3 ---------------------------------------------------------------------------------------
-constexpr int EMIT_TILE = 64;       // frames per block
-constexpr int EMIT_THREADS = 256;   // 8 warps; lane = packet of the group, warp = frame phase
-
-__device__ __forceinline__ void tile_put(uint8_t *row, int32_t lo_byte, int32_t hi_byte, int32_t off, int32_t v, int bps) {
-    // store the bps little-endian bytes of v at packet byte offset `off`, clipped to the tile [lo_byte, hi_byte)
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (k < bps) {
-            int32_t o = off + k;
-            if (o >= lo_byte && o < hi_byte) row[o - lo_byte] = (uint8_t)((uint32_t)v >> (8 * k));
-        }
-    }
-}
-
-// WriteStereo16/20/24/32 + WriteMono16/20/24/32 (matrix.go:30-301), ops replayed in element order so
-// later elements overwrite earlier ones exactly as the sequential reference does.
-__global__ void __launch_bounds__(EMIT_THREADS) alac_emit_kernel(const uint8_t *__restrict__ packed,
-                                                                 const uint64_t *__restrict__ offsets,
-                                                                 const uint32_t *__restrict__ sizes,
-                                                                 uint32_t npackets, DevConfig cfg,
-                                                                 const int32_t *__restrict__ scratch,
-                                                                 const PacketDesc *__restrict__ descs,
-                                                                 uint8_t *__restrict__ pcm_out, uint64_t out_stride,
-                                                                 uint32_t tiles_per_packet) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_nfinal[32];
-    __shared__ int32_t s_status[32];
-    const uint32_t group = blockIdx.x / tiles_per_packet;
-    const uint32_t tile = blockIdx.x % tiles_per_packet;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t fb = cfg.num_channels * cfg.bps;          // bytes per frame
-    const uint32_t row_words = (EMIT_TILE * fb) / 4u + 1u;   // odd => conflict-free lane-per-row access
-    const int32_t s0 = (int32_t)(tile * EMIT_TILE);
-    const int32_t lo_byte = s0 * (int32_t)fb, hi_byte = (s0 + EMIT_TILE) * (int32_t)fb;
-    const uint32_t pidx = group * 32u + lane;
-    const bool valid = pidx < npackets;
-
-    uint32_t *sw = reinterpret_cast<uint32_t *>(smem);
-    for (uint32_t i = threadIdx.x; i < row_words * 32u; i += EMIT_THREADS) sw[i] = 0;  // fresh make(), decoder.go:120
-    PacketDesc const *desc = descs + pidx;
-    int32_t st = ST_REF_PANIC;
-    uint32_t nops = 0;
-    if (valid) {
-        st = desc->status;
-        nops = st == ST_OK ? desc->nops : 0;
-        if (warp == 0) {
-            s_nfinal[lane] = desc->n_final;
-            s_status[lane] = st;
-        }
-    } else if (warp == 0) {
-        s_nfinal[lane] = 0;
-        s_status[lane] = ST_REF_PANIC;
-    }
-    __syncthreads();
-
-    uint8_t *row = smem + (size_t)lane * row_words * 4u;
-    const int32_t *sbase = scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
-    Packet pk{nullptr, 0};
-    if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
-    const int bps = (int)cfg.bps;
-    const bool depth20 = cfg.bit_depth == 20;
-    const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;  // 16/20-bit writers ignore the shift buffer
-
-#pragma unroll 1
-    for (uint32_t e = 0; e < 8; e++) {
-        if (e < nops) {
-            const OpDesc op = desc->ops[e];
-            const bool stereo = op.kind == 2;
-            const int32_t *su = sbase + (size_t)op.slot * cfg.frame_length * 32u;
-            const int32_t *sv = su + (size_t)cfg.frame_length * 32u;
-            const uint32_t sb = (merges_shift ? (uint32_t)op.shift : 0u) * 8u;
-            const int32_t mix_res = op.mix_res;
-            const uint32_t mix_bits = op.mix_bits;
-            // a pair mapped onto the last channel spills R into the next frame (matrix.go:44-48)
-            const bool spills = (uint32_t)op.out_chan + (stereo ? 2u : 1u) > cfg.num_channels;
-            const int32_t first = spills ? s0 - 1 : s0;
-            for (int32_t i = first + (int32_t)warp; i < s0 + EMIT_TILE; i += EMIT_THREADS / 32) {
-                if (i < 0 || (uint32_t)i >= op.n) continue;
-                int32_t left = su[(size_t)i * 32u], right = 0;
-                if (stereo) {
-                    right = sv[(size_t)i * 32u];
-                    if (mix_res != 0) {  // matrix.go:40-41
-                        const int32_t v = right;
-                        left = left + v - sar_go(mix_res * v, mix_bits);
-                        right = left - v;
-                    }
-                }
-                if (depth20) {
-                    left = (int32_t)((uint32_t)left << 4);
-                    right = (int32_t)((uint32_t)right << 4);
-                }
-                if (sb) {  // shift buffer merge, matrix.go:132-135, :270-272
-                    const uint32_t idx = stereo ? (uint32_t)i * 2u : (uint32_t)i;
-                    left = (int32_t)shl_go((uint32_t)left, sb) | (int32_t)pk_bits(pk, op.shift_bitpos + idx * sb, sb);
-                    if (stereo)
-                        right = (int32_t)shl_go((uint32_t)right, sb) |
-                                (int32_t)pk_bits(pk, op.shift_bitpos + (idx + 1u) * sb, sb);
-                }
-                const int32_t off = i * (int32_t)fb + (int32_t)op.out_chan * bps;
-                tile_put(row, lo_byte, hi_byte, off, left, bps);
-                if (stereo) tile_put(row, lo_byte, hi_byte, off + bps, right, bps);
-            }
-        }
-        __syncthreads();
-    }
-
-    // flush: one warp per packet row, coalesced. The whole tile is written so the packet's slot in
-    // pcm_out is fully defined: bytes past output[:n] (decoder.go:127) and failed packets read as zero.
-    const uint32_t tile_frames = min((uint32_t)EMIT_TILE, cfg.frame_length - (uint32_t)s0);
-    const uint32_t limit = tile_frames * fb;  // multiple of 4; multiple of 16 for a full tile
-    for (uint32_t r = warp; r < 32u; r += EMIT_THREADS / 32) {
-        const uint32_t p = group * 32u + r;
-        if (p >= npackets) continue;
-        int64_t nvalid = s_status[r] == ST_OK ? (int64_t)s_nfinal[r] * fb - lo_byte : 0;
-        nvalid = nvalid < 0 ? 0 : (nvalid > (int64_t)limit ? (int64_t)limit : nvalid);
-        uint32_t *src = sw + (size_t)r * row_words;
-        uint8_t *srcb = reinterpret_cast<uint8_t *>(src);
-        for (uint32_t b = (uint32_t)nvalid + lane; b < limit; b += 32u) srcb[b] = 0;
-        __syncwarp();
-        uint8_t *dst = pcm_out + (size_t)p * out_stride + (size_t)lo_byte;
-        const uint32_t nvec = limit >> 4;
-        if ((((uintptr_t)dst) & 15u) == 0) {
-            for (uint32_t v = lane; v < nvec; v += 32u) {
-                uint4 q = make_uint4(src[v * 4u], src[v * 4u + 1u], src[v * 4u + 2u], src[v * 4u + 3u]);
-                reinterpret_cast<uint4 *>(dst)[v] = q;
-            }
-        } else {
-            for (uint32_t w = lane; w < nvec * 4u; w += 32u) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
-        }
-        for (uint32_t w = nvec * 4u + lane; w < (limit >> 2); w += 32u) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
-    }
+    __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
+    // stage 3 reuses the ring / job / window memory as its transpose tile
+    EmitArgs ea{packed, offsets, sizes, npackets, scratch, descs, pcm_out, out_stride};
+    RoleTimer rt(lane, 8 + (int)warp);
+    const unsigned long long t_emit = rt.now();
+    emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
+    rt.add(0, t_emit);
+    rt.flush(1);
 }
 
 }  // namespace alacb200

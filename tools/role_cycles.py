@@ -14,7 +14,7 @@ d_packed = torch.from_numpy(wl['packed']).cuda(); d_off = torch.from_numpy(wl['o
 d_sz = torch.from_numpy(wl['sizes'].view(np.int32)).cuda(); d_pcm = torch.empty(n * stride, dtype=torch.uint8, device='cuda')
 d_nb = torch.zeros(n, dtype=torch.int32, device='cuda'); d_st = torch.zeros(n, dtype=torch.int32, device='cuda')
 nct = (n + 31) // 32
-buf = torch.zeros(nct * 8, dtype=torch.int64, device='cuda')
+buf = torch.zeros(nct * 16, dtype=torch.int64, device='cuda')
 def run():
     rc = pkg.lib.alacb200_decode_packets_device(dec._h, d_packed.data_ptr(), d_packed.numel(), d_off.data_ptr(), d_sz.data_ptr(), n,
                                                 d_pcm.data_ptr(), stride, d_nb.data_ptr(), d_st.data_ptr(), None)
@@ -24,11 +24,12 @@ f = pkg.lib.alacb200_debug_role_cycles; f.argtypes = [C.c_void_p]; f.restype = C
 assert f(buf.data_ptr()) == 0
 run(); run()
 f(None)
-b = buf.cpu().numpy().reshape(nct, 8).astype(np.float64)
-names = ['E total', 'E wait-empty', 'E top-up', 'P0 total', 'P0 wait-full', 'P1 total', 'P1 wait-full']
+b = buf.cpu().numpy().reshape(nct, 16).astype(np.float64)
+names = ['E total', 'E wait-empty', 'E top-up', 'P0 total', 'P0 wait-full', 'P1 total', 'P1 wait-full', 'tag', 'emit w0', 'emit w1', 'emit w2']
 for k, nm in enumerate(names):
+    if nm == 'tag': continue
     print(f'{nm:14s} mean {b[:,k].mean()/1e6:8.3f} Mcyc   max {b[:,k].max()/1e6:8.3f} Mcyc')
-tag = buf.cpu().numpy().reshape(nct, 8)[:, 7]
+tag = buf.cpu().numpy().reshape(nct, 16)[:, 7]
 smid, wid = tag >> 8, tag & 255
 import collections
 per_sm = collections.defaultdict(list)
