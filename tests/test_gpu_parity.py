@@ -126,3 +126,87 @@ def test_unaligned_offsets_and_wide_stride(pkg):
     got = b''.join(bytes(out[i, :nb[i]]) for i in range(len(packets)))
     assert np.array_equal(ol.pcm_bytes_to_int(got, 16, 2), x)
     assert (out[:, dec.frame_bytes:] == 0).all()
+
+
+def test_decoder_read_seek_m4a(pkg):
+    """NewDecoder/Read/Seek over an M4A (BASELINE configs[0] shape, shortened): conformance_test.go:282-292 (bit-for-bit
+    vs source) and :343-421 (seek at 0/25/50/75 % equals the tail of the full decode)."""
+    from m4a_writer import build_m4a
+    ocfg = ol.Config.make(bit_depth=16, num_channels=2, sample_rate=44100)
+    frames = 44100 * 6 + 321
+    x = make_signal('bench', 2, frames, 16, 44100, seed=1)
+    packets = ol.encode_stream(ocfg, x)
+    data, _ = build_m4a(ol.make_cookie(ocfg), packets, samples_per_chunk=7, last_frames=frames % 4096)
+    want = ol.int_to_pcm_bytes(x, 16)
+    dec = pkg.NewDecoder(data, window=16)
+    assert dec.Format() == pkg.PCMFormat(44100, 16, 2)
+    assert dec.Duration() == len(packets) * 4096 * 10**9 // 44100  # over-counts the partial last packet (decode.go:82-88)
+    got = b''
+    while True:
+        b = dec.Read(70001)
+        if not b:
+            break
+        got += b
+    assert got == want
+    assert dec.Read(10) == b''  # io.EOF stays EOF
+    for frac in (0.0, 0.25, 0.5, 0.75):
+        at = dec.Seek(int(dec.Duration() * frac))
+        assert at == dec.Position()
+        frame = dec.sampleIdx * 4096  # packet-aligned (decode.go:109-121); `at` is that frame in truncated nanoseconds
+        assert at == frame * 10**9 // 44100
+        assert dec.ReadAll() == want[frame * 4:]
+    assert dec.Seek(10 * dec.Duration()) == dec.Duration() and dec.Read(1) == b''
+    assert dec.Seek(-5) == 0
+
+
+def test_container_error_paths_on_gpu(pkg):
+    """error_test.go:368-442: garbage mdat -> success or ErrDecode, truncated packet -> any outcome but no crash."""
+    from m4a_writer import build_m4a
+    ocfg = ol.Config.make(bit_depth=16, num_channels=2, sample_rate=44100)
+    x = make_signal('music', 2, 4096 * 3, 16, 44100, seed=4)
+    packets = ol.encode_stream(ocfg, x)
+    data, samples = build_m4a(ol.make_cookie(ocfg), packets)
+    off, size = samples[1]
+    garbage = bytearray(data)
+    garbage[off:off + size] = np.random.default_rng(1).integers(0, 256, size, dtype=np.uint8).tobytes()
+    dec = pkg.NewDecoder(bytes(garbage))
+    try:
+        out = dec.ReadAll()
+        assert len(out) <= len(x) * 4
+    except pkg.ErrDecode as e:
+        assert 'decoding packet 1' in str(e)
+    # same statuses as the oracle for the damaged packet
+    st_o, _ = ol.decode_packet(ocfg, bytes(garbage[off:off + size]))
+    d = pkg.NewPacketDecoder(pkg.ParseMagicCookie(ol.make_cookie(ocfg)))
+    _, errs = d.DecodePackets([bytes(garbage[off:off + size])])
+    assert (errs[0].status if errs[0] else 0) == st_o
+    truncated = pkg.NewDecoder(data[:off + size // 2] + b'\0' * 16 + data[off + size // 2 + 16:])
+    try:
+        truncated.ReadAll()
+    except pkg.AlacError:
+        pass
+
+
+def test_full_size_c2_matches_oracle(pkg):
+    """BASELINE configs[1] at full size (14 063 packets, 345.6 MB of PCM): GPU PCM == oracle PCM, digest of the whole
+    stream, every packet OK, sizes add up."""
+    import bench
+    wl = bench.build_workload('c2', seed=2, threads=bench.host_cores())
+    n = len(wl['sizes'])
+    assert n == 14063
+    dec = pkg.NewPacketDecoder(pkg.ParseMagicCookie(wl['cookie']))
+    out, nb, st = dec.decode_packed(wl['packed'], wl['offsets'], wl['sizes'])
+    dec.close()
+    assert (st == 0).all()
+    assert int(nb.sum()) == wl['frames'] * 2 * 3
+    want, wnb, wst = ol.decode_batch(wl['cfg'], wl['packed'], wl['offsets'], wl['sizes'], nthreads=bench.host_cores())
+    assert (wst == 0).all() and np.array_equal(nb, wnb)
+    fb = wl['cfg'].frame_bytes()
+    assert np.array_equal(out[:, :fb], want)
+    h = hashlib.sha256()
+    for i in range(n):
+        h.update(out[i, :nb[i]].tobytes())
+    h2 = hashlib.sha256()
+    for i in range(n):
+        h2.update(want[i, :wnb[i]].tobytes())
+    assert h.hexdigest() == h2.hexdigest()
