@@ -260,6 +260,11 @@ int32_t alacb200_create(const alacb200_config *cfg, int device, alacb200_decoder
     dec->dev_cfg.pb = cfg->pb;
     dec->dev_cfg.mb = cfg->mb;
     dec->dev_cfg.kb = cfg->kb;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+        dec->dev_cfg.num_sms = (uint32_t)sms;
+    }
     dec->frame_bytes = (uint64_t)cfg->frame_length * cfg->num_channels * dec->dev_cfg.bps;
     cudaError_t e = cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
     if (!cuda_ok(e, "cudaFuncSetAttribute(alac_decode_kernel)")) {
@@ -465,6 +470,11 @@ const char *alacb200_last_error(void) { return g_last_error.c_str(); }
 
 // Developer hook (not part of include/alac_b200.h): point the decode kernel's per-role clock64 counters at a
 // device buffer of n_ctas*8 u64 (or NULL to switch them off). Used by tools/role_cycles.py.
+int32_t alacb200_debug_flags(unsigned int flags) {
+    CU(cudaMemcpyToSymbol(g_debug_flags, &flags, sizeof(flags)));
+    return ALACB200_OK;
+}
+
 int32_t alacb200_debug_role_cycles(unsigned long long *d_buf) {
     CU(cudaMemcpyToSymbol(g_role_cycles, &d_buf, sizeof(d_buf)));
     return ALACB200_OK;

@@ -46,6 +46,7 @@ struct DevConfig {
     uint32_t num_channels;
     uint32_t bps;
     uint32_t pb, mb, kb;
+    uint32_t num_sms;  // for spreading the role warps of co-resident CTAs over the SM sub-partitions
 };
 
 // What stage 1+2 hands to stage 3 for one decoded element (one "write op" of matrix.go).
@@ -58,13 +59,13 @@ struct OpDesc {
     uint8_t shift;          // bytesShifted seen by the writer (0 for escape elements)
     uint8_t mix_bits;
     int8_t mix_res;
-    uint16_t pad_;
+    uint16_t pad_;          // 1: the element was emitted live by the V predictor warp
 };
 struct PacketDesc {
     int32_t status;
     uint32_t n_final;
     uint32_t nops;
-    uint32_t pad_;
+    uint32_t pad_;          // frames already covered by live emission (multiple of 32)
     OpDesc ops[8];
 };
 
@@ -139,21 +140,27 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// backoff_ns > 0: sleep between polls, so a warp that is far ahead of its producer does not eat the issue slots of the
+// entropy warps sharing its SM sub-partition (a ring chunk takes ~8000 cycles to produce)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t backoff_ns = 0) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
-    do {
+    for (;;) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-    } while (!done);
+        if (done) break;
+        if (backoff_ns) __nanosleep(backoff_ns);
+    }
 }
 
 // Optional role timing (clock64 per role, lane 0): [cta][16] (8..10 = emit tail per warp), E total, E wait-empty, E top-up, P0 total, P0 wait,
 // P1 total, P1 wait, unused. Enabled by pointing g_role_cycles at a buffer (alacb200_debug_role_cycles).
 __device__ unsigned long long *g_role_cycles = nullptr;
+__device__ unsigned int g_sm_ticket[256];  // per-SM CTA counter (monotonic; only its value mod 4 is used)
+__device__ unsigned int g_debug_flags = 0;  // bit 0: no live emission (developer experiments)
 struct RoleTimer {
     unsigned long long *slot;
     unsigned long long acc[3] = {0, 0, 0};
@@ -171,17 +178,24 @@ struct RoleTimer {
 // residuals, 32 samples at a time, through a shared-memory ring to two PREDICTOR warps (lane = packet):
 // consumer 0 takes the mono / U stream of every element, consumer 1 the V stream. The serial entropy chain
 // of a packet (U then V, golomb.go) therefore overlaps with both predictor chains.
-constexpr int DEC_THREADS = 96;
+constexpr int DEC_THREADS = 128;
 constexpr int RING_SLOTS = 4;    // ring depth per consumer
 constexpr int CHUNK = 32;        // samples per ring slot
 constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged per lane (512 B window)
+constexpr int LIVE_SHIFT_CHUNKS = 10;  // 16-byte chunks covering 32 frames x 2 channels x 2 shift bytes at any alignment
 
 struct DecShared {
     int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (32 KB)
-    uint32_t job[2][RING_SLOTS][4][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax
+    uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
+                                             // live-emit word, shift bit position, U streams to wait for
     uint4 fifo[32][FIFO_CHUNKS + 1];         // compressed bytes staged by cp.async, [lane][chunk] (+1: bank skew)
     uint64_t full_bar[2][RING_SLOTS];
-    uint64_t empty_bar[2][RING_SLOTS];
+    uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
+    uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
+    // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
+    int32_t live_u[CHUNK][32];
+    uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
+    volatile uint32_t u_streams_done;  // streams the U/mono predictor warp has finished (release/acquire by fences)
 };
 
 // job meta word
@@ -423,6 +437,9 @@ struct StreamSpec {
     uint32_t pb_factor;
     uint32_t meta;         // job meta word for the consumer
     uint32_t coef_bitpos;  // where the consumer finds the 16-bit coefficients
+    uint32_t live;         // V of a pair in a 2-channel stream: bit 31 set, mixBits | mixRes<<8 | bytesShifted<<16
+    uint32_t shift_bitpos;
+    uint32_t u_streams;    // number of U/mono streams that must be finished before the last parked samples are read
 };
 
 // Produce one stream for consumer `cons`: ceil(nmax/32) ring slots (at least one: it carries the job).
@@ -460,11 +477,15 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
             sm.job[cons][slot][1][lane] = active ? sp.meta : (uint32_t)JOB_INACTIVE;
             sm.job[cons][slot][2][lane] = sp.coef_bitpos;
             sm.job[cons][slot][3][lane] = nmax;
+            sm.job[cons][slot][4][lane] = active ? sp.live : 0u;
+            sm.job[cons][slot][5][lane] = sp.shift_bitpos;
+            sm.job[cons][slot][6][lane] = sp.u_streams;
             if (pair) {
                 sm.job[1][slot2][0][lane] = sp2.n;
                 sm.job[1][slot2][1][lane] = active ? sp2.meta : (uint32_t)JOB_INACTIVE;
                 sm.job[1][slot2][2][lane] = sp2.coef_bitpos;
                 sm.job[1][slot2][3][lane] = nmax;
+                sm.job[1][slot2][4][lane] = 0u;  // escape pairs arrive interleaved: not emitted live
             }
         }
         int32_t *dst = &sm.ring[cons][slot][0][lane];
@@ -701,6 +722,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     bool parsing = valid;
     if (valid && pk.size > 0x0FFFFFFFu) { st = ST_REF_PANIC; parsing = false; }  // bit positions are 32-bit here
     uint32_t seq[2] = {0, 0};
+    uint32_t nstreams0 = 0;  // streams handed to the U/mono predictor warp so far
     BitReader br;
     br.fifo = fifo_addr;
     RoleTimer rt(lane, 0);
@@ -714,6 +736,14 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         if (!__any_sync(FULL_MASK, h.have)) break;
         const int32_t ctx = (h.stereo ? CTX_CPE : CTX_SCE) << 8;
         StreamSpec s0, s1;
+        s0.live = s1.live = 0;
+        s0.shift_bitpos = s1.shift_bitpos = 0;
+        s0.u_streams = s1.u_streams = 0;
+        // 2-channel streams whose 32 packets all carry one compressed pair: the V predictor warp emits PCM itself
+        const bool live_round = cfg.num_channels == 2u && !(g_debug_flags & 1u) &&
+                                __all_sync(FULL_MASK, !valid || (h.have && h.stereo && !h.escape && st == ST_OK &&
+                                                                 (h.num[1] == 0 || h.num[1] == 31 || h.num[1] == 8 ||
+                                                                  (h.num[1] >= 4 && h.num[1] <= 6))));
         s0.active = h.have;
         s1.active = h.have && h.stereo;
         s0.escape = s1.escape = h.escape;
@@ -759,6 +789,12 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                     st = ST_REF_PANIC | ctx;
             }
             const int32_t before = st;
+            if (pass != 1) nstreams0++;
+            if (pass == 1 && live_round) {
+                a.live = 0x80000000u | (h.mix_bits & 0xffu) | (((uint32_t)h.mix_res & 0xffu) << 8) | (h.shift << 16);
+                a.shift_bitpos = h.shift_bitpos;
+                a.u_streams = nstreams0;
+            }
             produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
                 if ((st & 0xff) == ST_REF_PANIC) st |= ctx;
@@ -791,7 +827,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                     op.shift = (uint8_t)(h.escape ? 0u : h.shift);
                     op.mix_bits = (uint8_t)h.mix_bits;
                     op.mix_res = (int8_t)h.mix_res;
-                    op.pad_ = 0;
+                    op.pad_ = live_round ? 1 : 0;  // already written to pcm_out by the V predictor warp
                     desc->ops[nops++] = op;
                     ns = h.n;
                     chan_idx += h.stereo ? 2u : 1u;
@@ -807,7 +843,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         uint32_t smid, wid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        rt.slot[7] = ((unsigned long long)smid << 8) | wid;
+        rt.slot[11] = ((unsigned long long)smid << 8) | wid;
     }
     // tell both predictor warps to leave
     for (int cons = 0; cons < 2; cons++) {
@@ -836,8 +872,303 @@ __device__ __forceinline__ int32_t delta_step(bool on, int32_t &prev, int32_t r,
 }
 
 struct Job {
-    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax;
+    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax, live, shift_bitpos, u_streams;
 };
+
+// sb (8 or 16) bits at bit offset `rel` of a staged shift row (bytes in stream order, 32-bit words as loaded)
+__device__ __forceinline__ uint32_t shift_field(const uint32_t *row_words, uint32_t rel, uint32_t sb) {
+    const uint32_t b = rel >> 3;
+    const uint32_t w0 = __byte_perm(row_words[b >> 2], 0, 0x0123);
+    const uint32_t w1 = __byte_perm(row_words[(b >> 2) + 1u], 0, 0x0123);
+    const uint32_t win = __funnelshift_l(w1, w0, (b & 3u) * 8u + (rel & 7u));  // < 32
+    return win >> (32u - sb);
+}
+
+// What the V predictor warp needs to emit PCM itself (2-channel streams).
+struct LiveCtx {
+    const int32_t *u_base;  // parked U samples of this group, [sample][lane]
+    uint8_t *slot;          // this lane's packet slot in pcm_out
+    PacketDesc *desc;
+    uint32_t frame_length, bps, bit_depth;
+    bool vec_ok, enabled;
+};
+
+// Start fetching what the emission of chunk `ck` needs: the parked U samples of the 32 frames (one 4 KB block,
+// cooperative) and this lane's shift bytes, all by cp.async so they land while the predictor runs.
+__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const LiveCtx &lc, const Packet &pk, uint32_t ck,
+                                              bool live_lane, uint32_t n_lane, uint32_t sb, uint32_t shift_bitpos,
+                                              uint32_t &rel0) {
+    const uint32_t base_i = ck * CHUNK;
+    const uint8_t *ug = reinterpret_cast<const uint8_t *>(lc.u_base + (size_t)base_i * 32u);
+    const uint32_t frames_left = lc.frame_length > base_i ? lc.frame_length - base_i : 0u;
+    const uint32_t ubase = smem_u32(&sm.live_u[0][0]);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t piece = k * 32u + lane;                  // 16-byte piece of the 4 KB block: frame = piece / 8
+        const uint32_t nb = (piece >> 3) < frames_left ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ubase + piece * 16u),
+                     "l"(ug + (nb ? (size_t)piece * 16u : 0)), "r"(nb)
+                     : "memory");
+    }
+    rel0 = 0;
+    const uint32_t cnt = (live_lane && n_lane > base_i) ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
+    if (sb && cnt) {
+        const uint32_t first_bit = shift_bitpos + base_i * 2u * sb;
+        const uint32_t nbytes = ((first_bit & 7u) + cnt * 2u * sb + 7u) / 8u + 2u;  // +2: the 24-bit window of BitBuffer.Read
+        const uint8_t *g0 = pk.p + (first_bit >> 3);
+        const uint8_t *ga = reinterpret_cast<const uint8_t *>(((uintptr_t)g0) & ~(uintptr_t)15);
+        const uint32_t lead = (uint32_t)(g0 - ga);
+        const uint32_t nchunks = (lead + nbytes + 15u) / 16u;  // <= LIVE_SHIFT_CHUNKS
+        const uint8_t *pend = pk.p + pk.size;
+        const uint32_t sbase = smem_u32(&sm.live_shift[lane][0]);
+#pragma unroll
+        for (uint32_t c = 0; c < LIVE_SHIFT_CHUNKS; c++) {
+            if (c < nchunks) {
+                const uint8_t *src = ga + c * 16u;
+                // bytes at or past the packet end arrive as zeros (bitbuffer.go:36-51)
+                const uint32_t nb = src >= pend ? 0u : (uint32_t)min((ptrdiff_t)16, pend - src);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + c * 16u), "l"(nb ? src : ga), "r"(nb)
+                             : "memory");
+            }
+        }
+        rel0 = lead * 8u + (first_bit & 7u);
+    }
+}
+
+// Generic (any depth / shift) emission of the 32 frames of chunk `ck` of a live pair: V from live_v, U from live_u, shift bytes from live_shift;
+// two batches of 16 frames, each leaving as 2*BPS 128-bit stores to the lane's own packet slot (matrix.go:30-215).
+template <int BPS>
+__device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
+                                          uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
+                                          const int32_t *vsrc) {
+    constexpr int FB = 2 * BPS;
+    constexpr int EB = 16;
+    const int32_t mix_res = (int32_t)(int8_t)((live_word >> 8) & 0xffu);
+    const uint32_t mix_bits = live_word & 0xffu;
+    const bool depth20 = lc.bit_depth == 20;
+    const uint32_t *shrow = reinterpret_cast<const uint32_t *>(&sm.live_shift[lane][0]);
+#pragma unroll 1
+    for (uint32_t half = 0; half < 2; half++) {
+        const uint32_t f0 = ck * CHUNK + half * EB;
+        if (f0 >= lc.frame_length) break;
+        const uint32_t cnt = n_lane > f0 ? min((uint32_t)EB, n_lane - f0) : 0u;
+        uint32_t ow[4 * FB];
+#pragma unroll
+        for (int k = 0; k < 4 * FB; k++) ow[k] = 0;
+#pragma unroll
+        for (int q = 0; q < EB; q++) {
+            const uint32_t jq = half * EB + (uint32_t)q;
+            int32_t left = sm.live_u[jq][lane], right = vsrc[jq * 32u];
+            if (mix_res != 0) {  // matrix.go:40-41
+                const int32_t v = right;
+                left = left + v - sar_go(mix_res * v, mix_bits);
+                right = left - v;
+            }
+            if (depth20) {
+                left = (int32_t)((uint32_t)left << 4);
+                right = (int32_t)((uint32_t)right << 4);
+            }
+            if (sb) {  // shift buffer merge, matrix.go:132-135
+                const uint32_t rel = rel0 + jq * 2u * sb;
+                left = (int32_t)shl_go((uint32_t)left, sb) | (int32_t)shift_field(shrow, rel, sb);
+                right = (int32_t)shl_go((uint32_t)right, sb) | (int32_t)shift_field(shrow, rel + sb, sb);
+            }
+            constexpr uint64_t lmask = BPS == 4 ? 0xffffffffull : ((1ull << (8 * BPS)) - 1ull);
+            uint64_t v = ((uint64_t)(uint32_t)left & lmask) | (((uint64_t)(uint32_t)right & lmask) << (8 * BPS));
+            if ((uint32_t)q >= cnt) v = 0;  // frames past the sample count stay zero (decoder.go:120, :127)
+            const int bit = q * FB * 8;
+            const int wi = bit / 32, sh = bit % 32;
+            ow[wi] |= (uint32_t)(v << sh);
+            if (sh + FB * 8 > 32) ow[wi + 1] |= (uint32_t)(v >> (32 - sh));
+            if (sh + FB * 8 > 64) ow[wi + 2] |= (uint32_t)(v >> (64 - sh));
+        }
+        if (live_lane) {
+            uint8_t *dst = lc.slot + (size_t)f0 * FB;
+            const uint32_t frames_here = min((uint32_t)EB, lc.frame_length - f0);
+            if (frames_here == EB && lc.vec_ok) {
+#pragma unroll
+                for (int k = 0; k < FB; k++)
+                    reinterpret_cast<uint4 *>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+            } else {
+                const uint32_t nb = frames_here * FB;  // a multiple of 4 (FB is even)
+#pragma unroll
+                for (int k = 0; k < 4 * FB; k++)
+                    if ((uint32_t)(4 * k + 4) <= nb) reinterpret_cast<uint32_t *>(dst)[k] = ow[k];
+            }
+        }
+    }
+}
+
+// un-mix of one frame (matrix.go:40-41; mixRes == 0 means plain L/R)
+__device__ __forceinline__ void unmix(int32_t u, int32_t v, int32_t mix_res, uint32_t mix_bits, int32_t &left, int32_t &right) {
+    const int32_t l = u + v - sar_go(mix_res * v, mix_bits);
+    left = mix_res != 0 ? l : u;
+    right = mix_res != 0 ? l - v : v;
+}
+
+// Store the packed words of 16 frames (NW4 x 16 bytes) to the lane's packet slot.
+template <int NW4>
+__device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint32_t fb, const uint32_t *ow, bool live_lane) {
+    if (!live_lane) return;
+    uint8_t *dst = lc.slot + (size_t)f0 * fb;
+    const uint32_t frames_here = min(16u, lc.frame_length - f0);
+    if (frames_here == 16u && lc.vec_ok) {
+#pragma unroll
+        for (int k = 0; k < NW4; k++)
+            reinterpret_cast<uint4 *>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
+    } else {
+        const uint32_t nb = frames_here * fb;  // a multiple of 4 for a pair
+#pragma unroll
+        for (int k = 0; k < 4 * NW4; k++)
+            if ((uint32_t)(4 * k + 4) <= nb) reinterpret_cast<uint32_t *>(dst)[k] = ow[k];
+    }
+}
+
+// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u, shift bytes from live_shift; two
+// batches of 16 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
+// The two shapes real streams have -- 16-bit, and 24-bit with one shifted byte -- are packed with byte permutes
+// (3 PRMT per 2 frames); everything else takes the generic path.
+template <int BPS>
+__device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
+                                          uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
+                                          const int32_t *vsrc) {
+    const bool fast = (BPS == 2 && lc.bit_depth == 16) || (BPS == 3 && lc.bit_depth == 24 && sb == 8u);
+    if (!__all_sync(FULL_MASK, fast)) {
+        live_emit_generic<BPS>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+        return;
+    }
+    const int32_t mix_res = (int32_t)(int8_t)((live_word >> 8) & 0xffu);
+    const uint32_t mix_bits = live_word & 0xffu;
+    const uint32_t *shrow = reinterpret_cast<const uint32_t *>(&sm.live_shift[lane][0]);
+#pragma unroll 1
+    for (uint32_t half = 0; half < 2; half++) {
+        const uint32_t f0 = ck * CHUNK + half * 16u;
+        if (f0 >= lc.frame_length) break;
+        const uint32_t cnt = n_lane > f0 ? min(16u, n_lane - f0) : 0u;
+        if (BPS == 3) {
+            // 16 frames x (1 byte L + 1 byte R) of shift data: 9 windows of 32 bits, two frames each
+            const uint32_t rel = rel0 + half * 256u;
+            const uint32_t wb = rel >> 5, bo = rel & 31u;
+            uint32_t W[10], S[9];
+#pragma unroll
+            for (int k = 0; k < 10; k++) W[k] = __byte_perm(shrow[wb + k], 0, 0x0123);
+#pragma unroll
+            for (int k = 0; k < 9; k++) S[k] = __funnelshift_l(W[k + 1], W[k], bo);
+            uint32_t ow[24];
+#pragma unroll
+            for (int pr = 0; pr < 8; pr++) {
+                uint32_t x24[4];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int q = 2 * pr + e;
+                    const uint32_t jq = half * 16u + (uint32_t)q;
+                    int32_t left, right;
+                    unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
+                    // (x << 8) | shift byte (matrix.go:132-135): frame 2k sits in the upper half of S[k], 2k+1 in the lower
+                    uint32_t l24 = __byte_perm(S[pr], (uint32_t)left, e == 0 ? 0x6543 : 0x6541);
+                    uint32_t r24 = __byte_perm(S[pr], (uint32_t)right, e == 0 ? 0x6542 : 0x6540);
+                    if ((uint32_t)q >= cnt) l24 = r24 = 0;  // frames past the sample count stay zero
+                    x24[2 * e] = l24;
+                    x24[2 * e + 1] = r24;
+                }
+                ow[3 * pr] = __byte_perm(x24[0], x24[1], 0x4210);      // L0 L0 L0 R0
+                ow[3 * pr + 1] = __byte_perm(x24[1], x24[2], 0x5421);  // R0 R0 L1 L1
+                ow[3 * pr + 2] = __byte_perm(x24[2], x24[3], 0x6542);  // L1 R1 R1 R1
+            }
+            store_batch<6>(lc, f0, 6u, ow, live_lane);
+        } else {
+            uint32_t ow[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const uint32_t jq = half * 16u + (uint32_t)q;
+                int32_t left, right;
+                unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
+                uint32_t w = __byte_perm((uint32_t)left, (uint32_t)right, 0x5410);
+                if ((uint32_t)q >= cnt) w = 0;
+                ow[q] = w;
+            }
+            store_batch<4>(lc, f0, 4u, ow, live_lane);
+        }
+    }
+}
+
+// EMIT warp (2-channel streams): follows consumer 1's ring behind the V predictor warp. For a live stream it turns every
+// slot (decoded V samples) plus the parked U samples and the shift bytes into interleaved PCM in pcm_out; for any other
+// stream it only hands the slot back. It is the last reader of consumer 1's slots.
+__device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
+                                          const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
+                                          uint32_t npackets, const DevConfig &cfg, const int32_t *__restrict__ scratch,
+                                          PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out, uint64_t out_stride) {
+    const uint32_t pidx = blockIdx.x * 32u + lane;
+    const bool valid = pidx < npackets;
+    Packet pk{packed, 0};
+    if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
+    LiveCtx lc;
+    lc.u_base = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u;  // slot 0 = U
+    lc.slot = pcm_out + (size_t)pidx * out_stride;
+    lc.desc = descs + pidx;
+    lc.frame_length = cfg.frame_length;
+    lc.bps = cfg.bps;
+    lc.bit_depth = cfg.bit_depth;
+    lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
+    lc.enabled = true;
+    RoleTimer rt(lane, 12);
+    const unsigned long long t_start = rt.now();
+    uint32_t seq = 0;
+#pragma unroll 1
+    for (;;) {
+        // first slot of a stream: its job
+        uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        unsigned long long tw = rt.now();
+        mbar_wait(&sm.vdone_bar[slot], par, 400);
+        rt.add(1, tw);
+        const uint32_t meta = sm.job[1][slot][1][lane];
+        if ((meta & 3u) == JOB_EXIT) break;
+        const uint32_t n = sm.job[1][slot][0][lane];
+        const uint32_t nmax = __shfl_sync(FULL_MASK, sm.job[1][slot][3][lane], 0);
+        const uint32_t live_word = sm.job[1][slot][4][lane];
+        const uint32_t shift_bitpos = sm.job[1][slot][5][lane];
+        const uint32_t u_streams = __shfl_sync(FULL_MASK, sm.job[1][slot][6][lane], 0);
+        const bool live_lane = valid && (meta & 3u) != JOB_INACTIVE && (live_word >> 31) != 0u;
+        const bool live_any = __any_sync(FULL_MASK, live_lane);
+        const uint32_t n_lane = live_lane ? n : 0u;
+        const uint32_t sb = (cfg.bit_depth == 24 || cfg.bit_depth == 32) ? ((live_word >> 16) & 3u) * 8u : 0u;
+        const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
+#pragma unroll 1
+        for (uint32_t ck = 0; ck < nchunks; ck++) {
+            slot = seq % RING_SLOTS;
+            par = (seq / RING_SLOTS) & 1u;
+            uint32_t rel0 = 0;
+            if (live_any) {
+                if (ck + 4u >= nchunks) {
+                    // the last parked U samples: the U predictor warp must have finished its stream
+                    while (sm.u_streams_done < u_streams) __nanosleep(64);
+                    __threadfence_block();
+                }
+                live_prefetch(sm, lane, lc, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
+            }
+            if (ck > 0) {
+                tw = rt.now();
+                mbar_wait(&sm.vdone_bar[slot], par, 400);
+                rt.add(1, tw);
+            }
+            if (live_any) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+                const int32_t *vsrc = &sm.ring[1][slot][0][lane];
+                if (cfg.bps == 3) live_emit<3>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+                else if (cfg.bps == 2) live_emit<2>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+                else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+                __syncwarp();
+            }
+            mbar_arrive(&sm.empty_bar[1][slot]);
+            seq++;
+        }
+        if (live_lane) lc.desc->pad_ = nchunks * CHUNK;  // frames written so far (zeros past the sample count)
+    }
+    rt.add(0, t_start);
+    rt.flush(2);
+}
 
 // Register predictor: orders 4/5/6/8 with int32 coefficients (unpcBlock4/5/6/8, predictor.go:99-618), plus
 // order 0 (copy, also escape pass-through) and order 31 (running sum), predictor.go:55-72. T = taps kept;
@@ -845,11 +1176,15 @@ struct Job {
 // their coefficients at zero and their LMS terms at zero. The body is branch-free; only the store is predicated.
 template <int T, bool MODE>
 __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
-                                           const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt) {
+                                           const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
+                                           const LiveCtx &lc) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
     const int32_t order = (int32_t)jb.order;
+    // live emission (2-channel streams): the decoded V samples replace the residuals in the ring slot, the emit
+    // warp takes them from there; decided per stream, uniform over the warp
+    const bool live_any = lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
     const bool fir_order = order == 4 || order == 5 || order == 6 || order == 8;
     const uint32_t fir_from = fir_order ? (uint32_t)order + 1u : 0xffffffffu;
     const bool copy = order == 0;  // order 0 copies; warm-up and order 31 accumulate
@@ -875,11 +1210,12 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
-            mbar_wait(&sm.full_bar[cons][slot], par);
+            mbar_wait(&sm.full_bar[cons][slot], par, 200);
             rt.add(1, tw);
         }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
-#pragma unroll 8
+        int32_t *vdst = &sm.ring[cons][slot][0][lane];
+#pragma unroll 4
         for (uint32_t j = 0; j < CHUNK; j++) {
             const uint32_t i = ck * CHUNK + j;
             int32_t r = src[j * 32];
@@ -924,9 +1260,11 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 #pragma unroll
             for (int t = T; t > 0; t--) h[t] = h[t - 1];
             h[0] = x;
-            if (i < n_lane) *outp = x;
+            if (live_any) vdst[j * 32] = x;
+            else if (i < n_lane) *outp = x;
             outp += 32;
         }
+        if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
     }
@@ -956,7 +1294,7 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
-            mbar_wait(&sm.full_bar[cons][slot], par);
+            mbar_wait(&sm.full_bar[cons][slot], par, 200);
             rt.add(1, tw);
         }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
@@ -994,6 +1332,7 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
                 dst[(size_t)i * 32u] = x;
             }
         }
+        if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
     }
@@ -1001,28 +1340,46 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
 
 __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int cons, const uint8_t *__restrict__ packed,
                                                const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
-                                               uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch) {
+                                               uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch,
+                                               PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out,
+                                               uint64_t out_stride) {
     const uint32_t pidx = blockIdx.x * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     int32_t *scratch_lane = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u + lane;
     uint32_t seq = 0;
+    LiveCtx lc;
+    lc.u_base = scratch_lane - lane;  // slot 0 of the group: the U channel of a 2-channel stream
+    lc.slot = pcm_out + (size_t)pidx * out_stride;
+    lc.desc = descs + pidx;
+    lc.frame_length = cfg.frame_length;
+    lc.bps = cfg.bps;
+    lc.bit_depth = cfg.bit_depth;
+    lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
+    lc.enabled = cons == 1 && cfg.num_channels == 2u;
+    uint32_t streams_done = 0;
     RoleTimer rt(lane, 3 + 2 * cons);
     const unsigned long long t_start = rt.now();
 #pragma unroll 1
     for (;;) {
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
         const unsigned long long tw = rt.now();
-        mbar_wait(&sm.full_bar[cons][slot], par);
+        mbar_wait(&sm.full_bar[cons][slot], par, 200);
         rt.add(1, tw);
         Job jb;
         jb.n = sm.job[cons][slot][0][lane];
         const uint32_t meta = sm.job[cons][slot][1][lane];
         jb.coef_bitpos = sm.job[cons][slot][2][lane];
         jb.nmax = sm.job[cons][slot][3][lane];
+        jb.live = sm.job[cons][slot][4][lane];
+        jb.shift_bitpos = sm.job[cons][slot][5][lane];
+        jb.u_streams = sm.job[cons][slot][6][lane];
         jb.kind = meta & 3u;
-        if (jb.kind == JOB_EXIT) break;  // written for every lane (the wait for it is idle time, not work)
+        if (jb.kind == JOB_EXIT) {  // written for every lane
+            if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);  // pass it on to the emit warp
+            break;
+        }
         jb.order = (meta >> 2) & 31u;
         jb.den = (meta >> 7) & 15u;
         jb.mode = (meta >> 11) & 1u;
@@ -1036,13 +1393,21 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
         const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
         if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt);
         else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
-            if (any8) stream_reg<8, true>(sm, lane, cons, seq, pk, jb, active, dst, rt);
-            else stream_reg<6, true>(sm, lane, cons, seq, pk, jb, active, dst, rt);
-        } else if (any8) stream_reg<8, false>(sm, lane, cons, seq, pk, jb, active, dst, rt);
-        else stream_reg<6, false>(sm, lane, cons, seq, pk, jb, active, dst, rt);
+            if (any8) stream_reg<8, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+            else stream_reg<6, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        } else if (any8) stream_reg<8, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        else stream_reg<6, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        if (cons == 0) {  // publish "this U/mono stream is parked" for the V warp's live emission
+            streams_done++;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                sm.u_streams_done = streams_done;
+            }
+        }
     }
     rt.add(0, t_start);
-    rt.flush(2);
+    rt.flush(3);
 }
 
 // ---- stage 3 ---------------------------------------------------------------------------------------
@@ -1073,15 +1438,6 @@ __device__ __forceinline__ void tile_put(uint8_t *row, int32_t lo_byte, int32_t 
             if (o >= lo_byte && o < hi_byte) row[o - lo_byte] = (uint8_t)((uint32_t)v >> (8 * k));
         }
     }
-}
-
-// sb (8 or 16) bits at bit offset `rel` of a staged shift row (bytes in stream order, 32-bit words as loaded)
-__device__ __forceinline__ uint32_t shift_field(const uint32_t *row_words, uint32_t rel, uint32_t sb) {
-    const uint32_t b = rel >> 3;
-    const uint32_t w0 = __byte_perm(row_words[b >> 2], 0, 0x0123);
-    const uint32_t w1 = __byte_perm(row_words[(b >> 2) + 1u], 0, 0x0123);
-    const uint32_t win = __funnelshift_l(w1, w0, (b & 3u) * 8u + (rel & 7u));  // < 32
-    return win >> (32u - sb);
 }
 
 // the little-endian bytes of one mono sample / one stereo pair into the transpose tile, widest aligned stores
@@ -1160,7 +1516,8 @@ __device__ __forceinline__ void emit_frames(const EmitOp &o, uint8_t *row, const
 // keep enough bytes in flight. Frames past the element's sample count are written as zeros (decoder.go:120, :127).
 template <int BPS, int WIDTH>
 __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
-                                            bool valid, const Packet &pk, const OpDesc &op, uint32_t n_final) {
+                                            bool valid, const Packet &pk, const OpDesc &op, uint32_t n_final,
+                                            uint32_t first_frame) {
     constexpr int FB = BPS * WIDTH;  // bytes per frame
     constexpr int EB = 16;           // frames per batch: 16*FB bytes = FB 128-bit stores
     constexpr uint32_t SROW = 21;    // shift words staged per lane and batch: 16 frames x 2 x 2 bytes + window + slack, odd
@@ -1256,7 +1613,7 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
             if (sh + FB * 8 > 64) ow[wi + 2] |= (uint32_t)(v >> (64 - sh));
         }
         // ---- store: FB x 16 bytes to the lane's own packet slot ---------------------------------------------------
-        if (valid) {
+        if (valid && f0 >= first_frame) {  // frames below first_frame were emitted live by the V predictor warp
             uint8_t *dst = slot + (size_t)f0 * FB;
             const uint32_t frames_here = min((uint32_t)EB, cfg.frame_length - f0);
             if (frames_here == EB && vec_ok) {
@@ -1319,15 +1676,21 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
         op0.n = 0; op0.shift_bitpos = 0; op0.kind = 0; op0.out_chan = 0; op0.slot = 0; op0.shift = 0; op0.mix_bits = 0; op0.mix_res = 0;
         if (nops == 1) op0 = desc->ops[0];
         const bool whole = cfg.num_channels <= 2u && (nops == 0 || (nops == 1 && op0.kind == cfg.num_channels && op0.out_chan == 0));
+        uint32_t first_frame = 0;
+        if (nops == 1 && op0.pad_ != 0) {  // emitted live: only frames the V warp did not reach are left (zeros)
+            first_frame = desc->pad_;
+            op0.n = 0;
+        }
+        if (__all_sync(FULL_MASK, !valid || first_frame >= cfg.frame_length)) return;  // nothing left to write
         if (__all_sync(FULL_MASK, whole)) {
             if (cfg.num_channels == 2u) {
-                if (cfg.bps == 3) emit_direct<3, 2>(x, cfg, group, smem, valid, pk, op0, n_final);
-                else if (cfg.bps == 2) emit_direct<2, 2>(x, cfg, group, smem, valid, pk, op0, n_final);
-                else emit_direct<4, 2>(x, cfg, group, smem, valid, pk, op0, n_final);
+                if (cfg.bps == 3) emit_direct<3, 2>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
+                else if (cfg.bps == 2) emit_direct<2, 2>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
+                else emit_direct<4, 2>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
             } else {
-                if (cfg.bps == 3) emit_direct<3, 1>(x, cfg, group, smem, valid, pk, op0, n_final);
-                else if (cfg.bps == 2) emit_direct<2, 1>(x, cfg, group, smem, valid, pk, op0, n_final);
-                else emit_direct<4, 1>(x, cfg, group, smem, valid, pk, op0, n_final);
+                if (cfg.bps == 3) emit_direct<3, 1>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
+                else if (cfg.bps == 2) emit_direct<2, 1>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
+                else emit_direct<4, 1>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
             }
             return;
         }
@@ -1459,7 +1822,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
 }
 
 // decodePacketInto for 32 packets per CTA, decoder.go:133-207: role warps (stages 1+2), then the whole CTA emits.
-__global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8_t *__restrict__ packed,
+__global__ void __launch_bounds__(DEC_THREADS, 3) alac_decode_kernel(const uint8_t *__restrict__ packed,
                                                                      const uint64_t *__restrict__ offsets,
                                                                      const uint32_t *__restrict__ sizes, uint32_t npackets,
                                                                      DevConfig cfg, int32_t *__restrict__ scratch,
@@ -1469,23 +1832,33 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
                                                                      int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t dec_smem[];
     DecShared &sm = *reinterpret_cast<DecShared *>(dec_smem);
+    __shared__ uint32_t s_rotation;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int c = 0; c < 2; c++)
             for (int s = 0; s < RING_SLOTS; s++) {
                 mbar_init(&sm.full_bar[c][s], 32);
-                mbar_init(&sm.empty_bar[c][s], 32);
+                mbar_init(&sm.empty_bar[c][s], c == 1 ? 64 : 32);
             }
+        for (int s = 0; s < RING_SLOTS; s++) mbar_init(&sm.vdone_bar[s], 32);
+        sm.u_streams_done = 0;
+        // CTAs that share an SM take consecutive tickets, whatever their block indices are: the hardware gives the
+        // four warps of a CTA to the four sub-partitions in order, so consecutive rotations keep e.g. the entropy warps
+        // of co-resident CTAs on different schedulers
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rotation = atomicAdd(&g_sm_ticket[smid & 255u], 1u);
     }
     __syncthreads();
     // rotate the roles over the warp slots so co-resident CTAs do not stack their entropy warps on one SMSP
-    const uint32_t role = (warp + blockIdx.x) % 3u;
+    const uint32_t role = (warp + s_rotation) % 4u;
     if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
-    else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch);
+    else if (role == 3) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
+    else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
     __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
     // stage 3 reuses the ring / job / window memory as its transpose tile
     EmitArgs ea{packed, offsets, sizes, npackets, scratch, descs, pcm_out, out_stride};
-    RoleTimer rt(lane, 8 + (int)warp);
+    RoleTimer rt(lane, 8 + (int)(warp % 3u));
     const unsigned long long t_emit = rt.now();
     emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
     rt.add(0, t_emit);

@@ -15,6 +15,9 @@ d_sz = torch.from_numpy(wl['sizes'].view(np.int32)).cuda(); d_pcm = torch.empty(
 d_nb = torch.zeros(n, dtype=torch.int32, device='cuda'); d_st = torch.zeros(n, dtype=torch.int32, device='cuda')
 nct = (n + 31) // 32
 buf = torch.zeros(nct * 16, dtype=torch.int64, device='cuda')
+import os
+if os.environ.get('ALAC_DEBUG_FLAGS'):
+    g = pkg.lib.alacb200_debug_flags; g.argtypes=[C.c_uint]; g.restype=C.c_int32; assert g(int(os.environ['ALAC_DEBUG_FLAGS'])) == 0
 def run():
     rc = pkg.lib.alacb200_decode_packets_device(dec._h, d_packed.data_ptr(), d_packed.numel(), d_off.data_ptr(), d_sz.data_ptr(), n,
                                                 d_pcm.data_ptr(), stride, d_nb.data_ptr(), d_st.data_ptr(), None)
@@ -25,11 +28,11 @@ assert f(buf.data_ptr()) == 0
 run(); run()
 f(None)
 b = buf.cpu().numpy().reshape(nct, 16).astype(np.float64)
-names = ['E total', 'E wait-empty', 'E top-up', 'P0 total', 'P0 wait-full', 'P1 total', 'P1 wait-full', 'tag', 'emit w0', 'emit w1', 'emit w2']
+names = ['E total', 'E wait-empty', 'E top-up', 'P0 total', 'P0 wait-full', 'P1 total', 'P1 wait-full', '-', 'tail w0', 'tail w1', 'tail w2', 'tag', 'EMIT total', 'EMIT wait']
 for k, nm in enumerate(names):
-    if nm == 'tag': continue
+    if nm in ('tag', '-'): continue
     print(f'{nm:14s} mean {b[:,k].mean()/1e6:8.3f} Mcyc   max {b[:,k].max()/1e6:8.3f} Mcyc')
-tag = buf.cpu().numpy().reshape(nct, 16)[:, 7]
+tag = buf.cpu().numpy().reshape(nct, 16)[:, 11]
 smid, wid = tag >> 8, tag & 255
 import collections
 per_sm = collections.defaultdict(list)
