@@ -185,18 +185,22 @@ constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged pe
 constexpr int LIVE_SHIFT_CHUNKS = 10;  // 16-byte chunks covering 32 frames x 2 channels x 2 shift bytes at any alignment
 
 struct DecShared {
+    // barriers first: stage 3 reuses everything behind them as its transpose tiles
+    uint64_t full_bar[2][RING_SLOTS];
+    uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
+    uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
+    volatile uint32_t u_streams_done;   // streams the U/mono predictor warp has finished (release/acquire by fences)
+    uint32_t pad_[27];                  // keeps `ring` 16-byte aligned: 160 + 4 + 108 = 272
     int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (32 KB)
     uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
                                              // live-emit word, shift bit position, U streams to wait for
     uint4 fifo[32][FIFO_CHUNKS + 1];         // compressed bytes staged by cp.async, [lane][chunk] (+1: bank skew)
-    uint64_t full_bar[2][RING_SLOTS];
-    uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
-    uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
     // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
     int32_t live_u[CHUNK][32];
     uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
-    volatile uint32_t u_streams_done;  // streams the U/mono predictor warp has finished (release/acquire by fences)
 };
+static_assert(offsetof(DecShared, ring) % 16 == 0, "ring must be 16-byte aligned");
+
 
 // job meta word
 enum : uint32_t { JOB_INACTIVE = 0, JOB_REG = 1, JOB_GENERIC = 2, JOB_EXIT = 3 };
@@ -1860,7 +1864,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 3) alac_decode_kernel(const uint8
     EmitArgs ea{packed, offsets, sizes, npackets, scratch, descs, pcm_out, out_stride};
     RoleTimer rt(lane, 8 + (int)(warp % 3u));
     const unsigned long long t_emit = rt.now();
-    emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
+    emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem + offsetof(DecShared, ring),
+                                 (uint32_t)(sizeof(DecShared) - offsetof(DecShared, ring)));
     rt.add(0, t_emit);
     rt.flush(1);
 }
