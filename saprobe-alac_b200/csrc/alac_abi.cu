@@ -358,8 +358,10 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
     if (!guard.ok) return ALACB200_E_CUDA;
 
     // Chunk the batch so copies of chunk k+1 / k-1 overlap the kernels of chunk k.
-    uint32_t chunk = (n + 5u) / 6u;
-    chunk = std::min(std::max(chunk, 1024u), 8192u);
+    uint32_t nchunks_target = 6;
+    if (const char *env = std::getenv("ALACB200_CHUNKS")) nchunks_target = (uint32_t)std::max(1, std::atoi(env));  // tuning knob
+    uint32_t chunk = (n + nchunks_target - 1u) / nchunks_target;
+    chunk = std::min(std::max(chunk, 512u), 16384u);
     const uint64_t max_chunk_pcm = 512ull << 20;
     while (chunk > 32u && (uint64_t)chunk * out_stride > max_chunk_pcm) chunk /= 2u;
     chunk = (chunk + 31u) & ~31u;

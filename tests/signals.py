@@ -6,6 +6,7 @@ make_signal(kind, channels, frames, bits, rate, seed) -> int64 [frames, channels
   silence_lsb  music with 25 % digital silence and 25 % +-2 LSB noise spliced in, so the Golomb
                zero-run (dynGet) and k==1 branches are exercised
   bench        music with 2 s silence + 2 s +-2 LSB noise in every 30 s (the section 8d recipe)
+  lsb          +-2 LSB noise only (the quiet-passage regime of the entropy coder)
   white        full-scale uniform noise (encoders fall back to escape elements)
   loud         near-full-scale two-tone with hard clipping and bursts (large residuals, escape codes)
 """
@@ -26,6 +27,8 @@ def _music(ch, n, bits, rate, rng, t0=0):
 def make_signal(kind, ch, n, bits, rate, seed, t0=0):
     rng = np.random.default_rng(seed)
     fs = 2 ** (bits - 1)
+    if kind == 'lsb':  # +-2 LSB noise only: the quiet-passage regime (one run-length code per sample)
+        return rng.integers(-2, 3, size=(n, ch), dtype=np.int64)
     if kind == 'white':
         return rng.integers(-fs, fs, size=(n, ch), dtype=np.int64)
     x = _music(ch, n, bits, rate, rng, t0)
