@@ -179,7 +179,7 @@ struct RoleTimer {
 // consumer 0 takes the mono / U stream of every element, consumer 1 the V stream. The serial entropy chain
 // of a packet (U then V, golomb.go) therefore overlaps with both predictor chains.
 constexpr int DEC_THREADS = 128;
-constexpr int RING_SLOTS = 4;    // ring depth per consumer
+constexpr int RING_SLOTS = 2;    // ring depth per consumer
 constexpr int CHUNK = 32;        // samples per ring slot
 constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged per lane (512 B window)
 constexpr int LIVE_SHIFT_CHUNKS = 10;  // 16-byte chunks covering 32 frames x 2 channels x 2 shift bytes at any alignment
@@ -1826,7 +1826,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
 }
 
 // decodePacketInto for 32 packets per CTA, decoder.go:133-207: role warps (stages 1+2), then the whole CTA emits.
-__global__ void __launch_bounds__(DEC_THREADS, 3) alac_decode_kernel(const uint8_t *__restrict__ packed,
+__global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8_t *__restrict__ packed,
                                                                      const uint64_t *__restrict__ offsets,
                                                                      const uint32_t *__restrict__ sizes, uint32_t npackets,
                                                                      DevConfig cfg, int32_t *__restrict__ scratch,
