@@ -210,3 +210,44 @@ def test_full_size_c2_matches_oracle(pkg):
     for i in range(n):
         h2.update(want[i, :wnb[i]].tobytes())
     assert h.hexdigest() == h2.hexdigest()
+
+
+def test_mixed_group_live_and_fallback(pkg):
+    """2-channel batch whose 32-packet groups mix pairs the emit warp writes live (orders 4-6/8) with packets that must fall
+    back (general orders, escape pairs, two SCEs, under-filled, mode != 0, partial frames, broken packets): every group
+    shape -- all live, none live, a lane failing mid-stream next to live lanes -- must give the oracle's bytes."""
+    ocfg = ol.Config.make(bit_depth=24, num_channels=2, sample_rate=96000)
+    rng = np.random.default_rng(31)
+    x = make_signal('silence_lsb', 2, 4096 * 12, 24, 96000, seed=12)
+    kinds = [ol.PacketOpts.make(), ol.PacketOpts.make(min_order=8, max_order=8), ol.PacketOpts.make(min_order=12, max_order=12),
+             ol.PacketOpts.make(force_escape=1), ol.PacketOpts.make(mode=2), ol.PacketOpts.make(bytes_shifted=0),
+             ol.PacketOpts.make(bytes_shifted=2, min_order=31, max_order=31), ol.PacketOpts.make(mix_bits=2, mix_res=-1)]
+    variants = [ol.encode_stream(ocfg, x, o) for o in kinds]
+    a = x[:4096, 0]
+    two_sce = ol.Writer(ocfg).element(0, a, order=4, coefs=[60, -30, 10, 5], bytes_shifted=1).element(0, a[::-1].copy(), order=6, coefs=[90, -45, 22, -11, 5, -2]).end().bytes()
+    under = ol.Writer(ocfg).element(0, a, order=5, coefs=[60, -30, 10, 5, 1]).end().bytes()
+    partial = ol.encode_packet(ocfg, x[:1234])
+    def batch(pick):
+        out = []
+        for i in range(32 * 9 + 5):
+            k = pick(i)
+            if k == 'two': out.append(two_sce)
+            elif k == 'under': out.append(under)
+            elif k == 'partial': out.append(partial)
+            elif k == 'broken':
+                p = bytearray(variants[0][i % 12]); p[len(p) // 2] ^= 0x5a; p = p[:len(p) - 7]; out.append(bytes(p))
+            else: out.append(variants[k][i % 12])
+        return out
+    # groups: 0 all live; 1 all order 8; 2 random mix of everything; 3 live + one broken lane; 4 live + partial; ...
+    def pick(i):
+        g, l = divmod(i, 32)
+        if g == 0: return 0
+        if g == 1: return 1
+        if g == 3: return 'broken' if l == 17 else 0
+        if g == 4: return 'partial' if l % 5 == 0 else 7
+        if g == 5: return 3
+        if g == 6: return 'two' if l % 2 else 'under'
+        return [0, 1, 2, 3, 4, 5, 6, 7, 'two', 'under', 'partial', 'broken'][int(rng.integers(0, 12))]
+    packets = batch(pick)
+    _, _, st = assert_parity(pkg, ocfg, packets, 'mixed groups')
+    assert (st != 0).any() and (st == 0).sum() > 200
