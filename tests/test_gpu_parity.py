@@ -4,6 +4,7 @@ Bit-exact: every packet's status word and every PCM byte must equal the oracle's
 the tolerance is zero.
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -251,3 +252,48 @@ def test_mixed_group_live_and_fallback(pkg):
     packets = batch(pick)
     _, _, st = assert_parity(pkg, ocfg, packets, 'mixed groups')
     assert (st != 0).any() and (st == 0).sum() > 200
+
+
+def test_full_size_c3_shift_buffer_stream(pkg):
+    """BASELINE configs[2] at full size: 1 h of 24-bit stereo 192 kHz, 168 750 packets, every element header carries
+    bytesShifted=1. Size-independent checks: every packet OK, byte count, and the digest of the whole PCM stream equals
+    the oracle's (decoded on all host cores)."""
+    import bench
+    wl = bench.build_workload('c3', seed=3, threads=bench.host_cores())
+    n = len(wl['sizes'])
+    assert n == 168750
+    # element header: tag(3) instance(4) unused(12) partial(1) shift(2) escape(1): shift = bits 20-21 of the packet
+    first = wl['packed'][wl['offsets'][::997].astype(np.int64) + 2]
+    assert (((first >> 2) & 3) == 1).all()
+    dec = pkg.NewPacketDecoder(pkg.ParseMagicCookie(wl['cookie']))
+    fb = wl['cfg'].frame_bytes()
+    out, nb, st = dec.decode_packed(wl['packed'], wl['offsets'], wl['sizes'], out=np.empty((n, fb), dtype=np.uint8), out_stride=fb)
+    dec.close()
+    assert (st == 0).all()
+    assert int(nb.astype(np.int64).sum()) == wl['frames'] * 2 * 3
+    want, wnb, wst = ol.decode_batch(wl['cfg'], wl['packed'], wl['offsets'], wl['sizes'], nthreads=bench.host_cores(),
+                                     out=np.empty((n, fb), dtype=np.uint8))
+    assert (wst == 0).all() and np.array_equal(nb, wnb)
+    assert hashlib.sha256(out[:n - 1].tobytes()).hexdigest() == hashlib.sha256(want[:n - 1].tobytes()).hexdigest()
+    assert np.array_equal(out[n - 1, :nb[n - 1]], want[n - 1, :nb[n - 1]])
+
+
+def test_cli_twin_wav_and_pcm(pkg, tmp_path):
+    """tools/alac_decode.py mirrors cmd/alac-example-decoder (example_decoder_test.go:35-131): PCM output equals the
+    source, WAV output is a 44-byte header + the same PCM."""
+    import subprocess
+    import sys
+    from m4a_writer import build_m4a
+    ocfg = ol.Config.make(bit_depth=16, num_channels=2, sample_rate=44100)
+    x = make_signal('music', 2, 4096 * 4 + 99, 16, 44100, seed=8)
+    data, _ = build_m4a(ol.make_cookie(ocfg), ol.encode_stream(ocfg, x), last_frames=99)
+    f = tmp_path / 't.m4a'
+    f.write_bytes(data)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, 'tools', 'alac_decode.py')
+    pcm = subprocess.run([sys.executable, cli, '-format', 'pcm', str(f)], capture_output=True, check=True).stdout
+    want = ol.int_to_pcm_bytes(x, 16)
+    assert pcm == want
+    wav = subprocess.run([sys.executable, cli, '-'], input=data, capture_output=True, check=True)
+    assert wav.stdout[:4] == b'RIFF' and wav.stdout[8:16] == b'WAVEfmt ' and wav.stdout[44:] == want
+    assert b'44100 Hz, 16-bit, 2 channel' in wav.stderr
