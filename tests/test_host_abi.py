@@ -139,3 +139,11 @@ def test_mp4_error_paths(pkg):
     j = data.index(b'stco')
     with pytest.raises(pkg.ErrNoTrack):
         pkg.FindALACTrack(data[:j] + b'xtco' + data[j + 4:])
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    """No silent fallback: without libalacb200.so the package refuses to import (and says how to build it)."""
+    monkeypatch.setattr(pkg, 'LIB_PATH', os.path.join(ROOT, 'saprobe-alac_b200', 'does_not_exist.so'))
+    with pytest.raises(ImportError) as ei:
+        pkg._load()
+    assert 'no CPU fallback' in str(ei.value)
