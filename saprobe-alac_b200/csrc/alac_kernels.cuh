@@ -1178,7 +1178,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
 // order 0 (copy, also escape pass-through) and order 31 (running sum), predictor.go:55-72. T = taps kept;
 // a lane whose order is below T runs with its upper taps' history differences forced to zero, which keeps
 // their coefficients at zero and their LMS terms at zero. The body is branch-free; only the store is predicated.
-template <int T, bool MODE>
+template <int T, bool MODE, bool LIVE>
 __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
                                            const LiveCtx &lc) {
@@ -1188,7 +1188,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
     const int32_t order = (int32_t)jb.order;
     // live emission (2-channel streams): the decoded V samples replace the residuals in the ring slot, the emit
     // warp takes them from there; decided per stream, uniform over the warp
-    const bool live_any = lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
+    constexpr bool live_any = LIVE;
     const bool fir_order = order == 4 || order == 5 || order == 6 || order == 8;
     const uint32_t fir_from = fir_order ? (uint32_t)order + 1u : 0xffffffffu;
     const bool copy = order == 0;  // order 0 copies; warm-up and order 31 accumulate
@@ -1219,7 +1219,8 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
         }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
         int32_t *vdst = &sm.ring[cons][slot][0][lane];
-#pragma unroll 4
+// unroll 2, not more: the entropy warps sharing the SM pay for every extra KB of hot code in instruction fetch
+#pragma unroll 2
         for (uint32_t j = 0; j < CHUNK; j++) {
             const uint32_t i = ck * CHUNK + j;
             int32_t r = src[j * 32];
@@ -1395,12 +1396,20 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
         const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
         const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
         const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
+        // live emission (2-channel streams, V warp): decided per stream by the entropy warp, uniform over the warp
+        const bool live = lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
         if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt);
         else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
-            if (any8) stream_reg<8, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-            else stream_reg<6, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        } else if (any8) stream_reg<8, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        else stream_reg<6, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+            if (live) {
+                if (any8) stream_reg<8, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+                else stream_reg<6, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+            } else if (any8) stream_reg<8, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+            else stream_reg<6, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        } else if (live) {
+            if (any8) stream_reg<8, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+            else stream_reg<6, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        } else if (any8) stream_reg<8, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        else stream_reg<6, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
         if (cons == 0) {  // publish "this U/mono stream is parked" for the V warp's live emission
             streams_done++;
             __syncwarp();
