@@ -146,6 +146,19 @@ int32_t launch(alacb200_decoder *dec, Work &work, const uint8_t *d_packed, const
                int32_t *d_status, cudaStream_t stream) {
     if (n == 0) return ALACB200_OK;
     const DevConfig &c = dec->dev_cfg;
+    // Bound the parked-sample scratch: very large batches (a library shard is millions of packets) run as a
+    // sequence of launches on the same stream, each reusing the scratch of the one before it.
+    const uint64_t per_group = (uint64_t)c.num_channels * c.frame_length * 32u * sizeof(int32_t);
+    const uint32_t max_groups = (uint32_t)std::max<uint64_t>(64, (8ull << 30) / per_group);
+    if ((n + 31u) / 32u > max_groups) {
+        for (uint32_t a = 0; a < n; a += max_groups * 32u) {
+            const uint32_t m = std::min(n - a, max_groups * 32u);
+            int32_t rc = launch(dec, work, d_packed, d_offsets + a, d_sizes + a, m, d_pcm + (size_t)a * out_stride, out_stride,
+                                d_out_bytes + a, d_status + a, stream);
+            if (rc != ALACB200_OK) return rc;
+        }
+        return ALACB200_OK;
+    }
     const uint32_t groups = (n + 31u) / 32u;
     const size_t scratch_bytes = (size_t)groups * c.num_channels * c.frame_length * 32u * sizeof(int32_t);
     if (scratch_bytes > work.scratch.cap || (size_t)n * sizeof(PacketDesc) > work.descs.cap) {

@@ -297,3 +297,33 @@ def test_cli_twin_wav_and_pcm(pkg, tmp_path):
     wav = subprocess.run([sys.executable, cli, '-'], input=data, capture_output=True, check=True)
     assert wav.stdout[:4] == b'RIFF' and wav.stdout[8:16] == b'WAVEfmt ' and wav.stdout[44:] == want
     assert b'44100 Hz, 16-bit, 2 channel' in wav.stderr
+
+
+def test_huge_batch_runs_as_several_launches(pkg):
+    """More packet groups than the scratch cap allows in one launch (8 GB / (channels * frame_length * 128 B)): the device
+    path splits into stream-ordered launches reusing the scratch; results must not depend on where the cuts fall."""
+    import torch
+    ocfg = ol.Config.make(bit_depth=16, num_channels=8, sample_rate=48000, frame_length=65536)
+    x = make_signal('music', 8, 65536 * 2, 16, 48000, seed=21)
+    base = ol.encode_stream(ocfg, x)
+    n = 32 * 128 * 2 + 45  # cap = 8 GB / (8 * 65536 * 128 B) = 128 groups -> 3 launches
+    packets = [base[i % 2] for i in range(n)]
+    dec = pkg.NewPacketDecoder(to_pkg_cfg(pkg, ocfg), 0)
+    packed, offs, sizes = pkg.pack_packets(packets)
+    stride = dec.frame_bytes
+    d_packed = torch.from_numpy(packed).cuda()
+    d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+    d_sz = torch.from_numpy(sizes.view(np.int32)).cuda()
+    d_pcm = torch.empty(n * stride, dtype=torch.uint8, device='cuda')
+    d_nb = torch.zeros(n, dtype=torch.int32, device='cuda')
+    d_st = torch.full((n,), -1, dtype=torch.int32, device='cuda')
+    rc = pkg.lib.alacb200_decode_packets_device(dec._h, d_packed.data_ptr(), d_packed.numel(), d_off.data_ptr(), d_sz.data_ptr(), n,
+                                                d_pcm.data_ptr(), stride, d_nb.data_ptr(), d_st.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert int((d_st != 0).sum()) == 0 and int((d_nb != stride).sum()) == 0
+    want = [torch.frombuffer(bytearray(ol.decode_packet(ocfg, base[k])[1]), dtype=torch.uint8).cuda() for k in range(2)]
+    rows = d_pcm.view(n, stride)
+    for i in list(range(0, n, 211)) + [n - 1, 4095, 4096, 4097, 8191, 8192]:
+        assert torch.equal(rows[i], want[i % 2]), i
+    dec.close()
