@@ -134,6 +134,7 @@ __device__ __forceinline__ uint32_t cur_read_one(const Packet &pk, Cursor &c) { 
 
 // ---- mbarrier (shared-memory producer/consumer barriers between the role warps) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v)); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -219,6 +220,13 @@ constexpr uint32_t FIFO_LANE_BYTES = FIFO_CHUNKS * 16 + 16;  // 528: +16 skews t
 __device__ __forceinline__ uint32_t clz_nz(uint32_t x) {
     uint32_t r;
     asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+// index of the highest set bit (31 - clz) in one instruction (FLO.U32); x != 0
+__device__ __forceinline__ uint32_t bit_index(uint32_t x) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
 }
 
@@ -429,7 +437,8 @@ __constant__ int8_t k_layout[8][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 
 // ====================================================================================================
 constexpr uint32_t FULL_MASK = 0xffffffffu;
 
-enum : uint32_t { BUSY_ESCAPE = 2, BUSY_LONG_CODES = 4, BUSY_DEAD = 8 };
+enum : uint32_t { BUSY_ESCAPE = 2, BUSY_LONG_CODES = 4, BUSY_DEAD = 8, BUSY_PARTIAL = 16 };
+constexpr uint32_t ZRUN_PARKED = 0x40000000u;  // "zero run" of a lane that has nothing (left) to decode
 
 // What one lane needs to produce one stream (a channel of a compressed element, or the raw samples of an
 // escape element).
@@ -492,11 +501,15 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                 sm.job[1][slot2][4][lane] = 0u;  // escape pairs arrive interleaved: not emitted live
             }
         }
-        int32_t *dst = &sm.ring[cons][slot][0][lane];
-        int32_t *dst2 = &sm.ring[1][slot2][0][lane];
+        const uint32_t a_dst = smem_u32(&sm.ring[cons][slot][0][lane]);
+        const uint32_t a_pair = smem_u32(&sm.ring[1][slot2][0][lane]) - a_dst;
         // samples of this lane inside this chunk
         const uint32_t base_i = c * CHUNK;
         const uint32_t cnt = (active && sp.n > base_i) ? min((uint32_t)CHUNK, sp.n - base_i) : 0u;
+        const uint32_t a_last = a_dst + (sp.n - 1u - base_i) * 128u;  // ring address of the stream's last sample, if it is in this chunk
+        // a lane with a short last chunk stops in the middle of it: the warp takes the general step for this chunk
+        busy = (busy & ~BUSY_PARTIAL) | ((cnt != 0u && cnt != (uint32_t)CHUNK) ? BUSY_PARTIAL : 0u);
+        if (cnt == 0u) e.zrun = ZRUN_PARKED;  // nothing (left) to decode: idle without touching bp
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; half++) {
             // keep the staged window ahead of the reader: 16 samples eat at most 16 x 67 bits = 9 chunks of 16
@@ -506,81 +519,107 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                 br.top_up();
                 rt.add(2, tt);
             }
+            // The hot loop below is straight-line for the whole warp; it is left (uniformly) for the general step of one
+            // sample, or for run-length codes the straight-line form does not cover, and entered again.
+            // the loop counter is the shared-memory address of the lane's ring entry: sample j lives at a_dst + 128 j
+            uint32_t aj = a_dst + half * (CHUNK / 2) * 128u;
+            const uint32_t a_end = aj + (CHUNK / 2) * 128u;
+#pragma unroll 1
+            while (aj != a_end) {
+                uint32_t left = 0;  // 1: sample j needs the general step; 2: lanes in `pend` owe a run-length code
+                bool pend = false;
 #pragma unroll 2
-            for (uint32_t jj = 0; jj < CHUNK / 2; jj++) {
-                const uint32_t j = half * (CHUNK / 2) + jj;
-                const uint32_t i = base_i + j;
-                br.begin_sample();
-                // ---- speculative decode of one ordinary code (golomb.go:172-201), straight-line ----------
-                const uint32_t w = br.window();
-                const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
-                uint32_t k = 31u - clz_nz((e.mean >> 9) + 3u);
-                k = min(k, e.kb);
-                const uint32_t mm = shl_go(1u, k) - 1u;
-                const uint32_t sfx = w << ((pre + 1u) & 31u);
-                const uint32_t v = shr_go(sfx, 32u - k);  // k == 0 (cookie kb 0) shifts by 32 -> 0
-                const bool big = v >= 2u;                 // v < 2: no suffix value, one bit goes back
-                const uint32_t nb = pre + k + (big ? 1u : 0u);
-                const uint32_t r = pre * mm + (big ? v - 1u : 0u);
-                // anything else goes through the general step: zero-run start / continuation, idle or failed
-                // lane, escape code, escape element, packet overrun, cookies whose codes can exceed one refill
-                const bool ordinary = ((e.zrun | busy) == 0u) & (j < cnt) & (pre < 9u) & (bp < e.size8);
-                int32_t res = 0, res2 = 0;
-                if (ordinary) {
-                    br.commit(br.sh + nb);  // kb <= 22 here: nb <= 31, one refill at most
+                for (; aj != a_end; aj += 128u) {
+                    br.begin_sample();
+                    // ---- one ordinary code (golomb.go:172-201), decoded by every lane whether it wants it or not ----
+                    const uint32_t w = br.window();
+                    const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
+                    const uint32_t k = min(bit_index((e.mean >> 9) + 3u), e.kb);
+                    const uint32_t pre1 = pre + 1u;
+                    const uint32_t v = __funnelshift_l(shl_go(w, pre1), 0u, k);  // the k bits after the prefix; k == 0 -> 0
+                    // prefix * (2^k - 1) + (v >= 2 ? v - 1 : 0): v < 2 means "no suffix value" and gives one bit back
+                    const uint32_t r = shl_go(pre, k) - pre1 + max(v, 1u);
+                    const uint32_t nb0 = pre + k + (v >= 2u ? 1u : 0u);
+                    // A lane inside a zero run (clear(predCoefs[count:end]), golomb.go:237) -- or parked in an endless
+                    // one because it has nothing left to decode -- consumes nothing and produces 0 with the same
+                    // instructions. Anything else (escape code, escape element, packet overrun, a saturating mean,
+                    // cookies whose codes can exceed one refill, a short last chunk) sends the WARP to the general step.
+                    const bool inrun = e.zrun != 0u;
+                    const bool ok = inrun | ((busy == 0u) & (pre < 9u) & (bp < e.size8) & (r <= 0xffffu));
+                    if (!__all_sync(FULL_MASK, ok)) {
+                        left = 1;
+                        break;
+                    }
+                    const uint32_t nb = inrun ? 0u : nb0;  // kb <= 22 here: nb <= 31, one refill at most
+                    const uint32_t nd = inrun ? 0u : r + e.zmode;
+                    br.commit(br.sh + nb);
                     bp += nb;
-                    const uint32_t nd = r + e.zmode;
-                    res = (int32_t)((nd >> 1) ^ (0u - (nd & 1u)));  // == ((nd+1)>>1) * (1 - 2*(nd&1)) for nd < 2^32-1
-                    uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
-                    if (r > 0xffffu) mean2 = 0xffffu;
+                    const uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
                     e.mean = mean2;
-                    e.zmode = 0;
-                    if (zero_run_due(mean2, i, sp.n)) {
-                        // the run-length code that follows (dynGet, golomb.go:112-144, :220-245), straight-line
+                    e.zmode = inrun ? e.zmode : 0u;
+                    e.zrun = inrun ? e.zrun - 1u : 0u;
+                    sts32(aj, (int32_t)((nd >> 1) ^ (0u - (nd & 1u))));  // == ((nd+1)>>1) * (1 - 2*(nd&1)) for nd < 2^32-1
+                    if (pair) sts32(aj + a_pair, 0);
+                    const bool zdue = !inrun & ((mean2 << 2) < 512u) & (aj != a_last);  // golomb.go:220
+                    if (__any_sync(FULL_MASK, zdue)) {
+                        // the run-length code that follows (dynGet, golomb.go:112-144, :220-245), branch-free
                         int32_t k32 = __clz((int32_t)mean2) - 24 + (int32_t)((mean2 + 16u) >> 6);
                         k32 = max(k32, 0);
-                        if (k32 > 16 || (bp >> 3) > pk.size) {  // never for a sane mean / position: general code
-                            if (!zero_run_start(pk, br, bp, e, i, sp.n, st)) {
-                                active = false;
-                                busy |= BUSY_DEAD;
-                            }
-                        } else {
-                            const uint32_t nxt2 = br.load(br.qn);  // the word after lo, should the first code have refilled
-                            const uint32_t mz = ((1u << k32) - 1u) & e.wb;
-                            const uint32_t w2 = br.window();
-                            const uint32_t pre2 = clz_nz(~w2);
-                            const bool esc2 = pre2 >= 9u;
-                            const uint32_t val = shr_go(w2 << ((pre2 + 1u) & 31u), 32u - (uint32_t)k32);
-                            const bool big2 = val >= 2u;
-                            const uint32_t run = esc2 ? ((w2 << 9) >> 16) : pre2 * mz + (big2 ? val - 1u : 0u);
-                            const uint32_t nb2 = esc2 ? 25u : pre2 + (uint32_t)k32 + (big2 ? 1u : 0u);
-                            br.nxt = nxt2;
-                            br.commit(br.sh + nb2);  // nb2 <= 26: one refill at most
-                            bp += nb2;
-                            if (i + 1u + run > sp.n) {  // golomb.go:232-234
-                                st = ST_SAMPLE_OVERRUN;
-                                active = false;
-                                busy |= BUSY_DEAD;
-                            }
-                            e.zrun = run;
-                            e.zmode = run >= 65535u ? 0u : 1u;
-                            e.mean = 0;
+                        pend = zdue & ((k32 > 16) | ((bp >> 3) > pk.size));  // never for a sane mean / position
+                        const bool go = zdue & !pend;
+                        const uint32_t nxt2 = br.load(br.qn);  // the word after lo, should the first code have refilled
+                        const uint32_t mz = ((1u << (k32 & 31)) - 1u) & e.wb;
+                        const uint32_t w2 = br.window();
+                        const uint32_t pre2 = clz_nz(~w2);
+                        const bool esc2 = pre2 >= 9u;
+                        const uint32_t val = __funnelshift_l(shl_go(w2, pre2 + 1u), 0u, (uint32_t)k32);
+                        const bool big2 = val >= 2u;
+                        const uint32_t run = esc2 ? ((w2 << 9) >> 16) : pre2 * mz + (big2 ? val - 1u : 0u);
+                        const uint32_t nb2 = esc2 ? 25u : pre2 + (uint32_t)k32 + (big2 ? 1u : 0u);
+                        br.nxt = nxt2;
+                        br.commit(br.sh + (go ? nb2 : 0u));  // nb2 <= 26: one refill at most
+                        bp += go ? nb2 : 0u;
+                        const bool over = go & (run > ((a_last - aj) >> 7));  // i + 1 + run > n, golomb.go:232-234
+                        e.zrun = over ? ZRUN_PARKED : go ? run : e.zrun;
+                        e.zmode = go ? (run >= 65535u ? 0u : 1u) : e.zmode;
+                        e.mean = go ? 0u : e.mean;
+                        st = over ? (int32_t)ST_SAMPLE_OVERRUN : st;
+                        active = active & !over;
+                        busy |= over ? (uint32_t)BUSY_DEAD : 0u;
+                        if (__any_sync(FULL_MASK, pend)) {
+                            left = 2;
+                            aj += 128u;
+                            break;
                         }
                     }
-                } else if (j < cnt && !(busy & BUSY_DEAD)) {
-                    if (e.zrun > 0u && busy == 0u) {  // inside a zero run (clear(predCoefs[count:end]), golomb.go:237)
-                        e.zrun--;
-                    } else if (sp.escape) {
-                        res = escape_sample(br, sp.chan_bits);
-                        if (pair) res2 = escape_sample(br, sp.chan_bits);
-                    } else if (!entropy_next(pk, br, bp, e, i, sp.n, res, st)) {
+                }
+                const uint32_t j = (aj - a_dst) >> 7;
+                if (left == 1) {
+                    const uint32_t i = base_i + j;
+                    int32_t res = 0, res2 = 0;
+                    if (j < cnt && !(busy & BUSY_DEAD)) {
+                        if (e.zrun > 0u && (busy & ~BUSY_PARTIAL) == 0u) {  // inside a zero run
+                            e.zrun--;
+                        } else if (sp.escape) {
+                            res = escape_sample(br, sp.chan_bits);
+                            if (pair) res2 = escape_sample(br, sp.chan_bits);
+                        } else if (!entropy_next(pk, br, bp, e, i, sp.n, res, st)) {
+                            active = false;
+                            busy |= BUSY_DEAD;  // a failed lane idles through the rest of the stream
+                            e.zrun = ZRUN_PARKED;
+                            res = 0;
+                        }
+                    }
+                    sts32(aj, res);
+                    if (pair) sts32(aj + a_pair, res2);
+                    aj += 128u;
+                } else if (left == 2) {
+                    if (pend && !zero_run_start(pk, br, bp, e, base_i + j - 1u, sp.n, st)) {
                         active = false;
-                        busy |= BUSY_DEAD;  // a failed lane idles through the rest of the stream
-                        res = 0;
+                        busy |= BUSY_DEAD;
+                        e.zrun = ZRUN_PARKED;
                     }
                 }
-                dst[j * 32] = res;
-                if (pair) dst2[j * 32] = res2;
             }
         }
         mbar_arrive(&sm.full_bar[cons][slot]);
