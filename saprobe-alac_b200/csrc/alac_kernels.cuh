@@ -236,7 +236,7 @@ struct BitReader {
     uint32_t fifo;         // shared address of this lane's window (FIFO_CHUNKS x 16 bytes)
     uint32_t req;          // next 16-byte chunk to request
     uint32_t qn;           // index (32-bit words from gbase) of the next word to load; hi = qn-2, lo = qn-1
-    uint32_t hi, lo, nxt;  // big-endian-converted words
+    uint32_t hi, lo;       // big-endian-converted words
     uint32_t sh;           // bits of hi already consumed (0..31)
 
     __device__ __forceinline__ void request(uint32_t c) {
@@ -276,18 +276,17 @@ struct BitReader {
         hi = load(q);
         lo = load(q + 1u);
         qn = q + 2u;
-        nxt = load(qn);
     }
-    // top of every sample iteration: (re)load the word after lo; its latency hides behind the decode
-    __device__ __forceinline__ void begin_sample() { nxt = load(qn); }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, sh); }
-    // first consume of an iteration, branch-free: sh2 = sh + bits consumed, must be < 64
-    __device__ __forceinline__ void commit(uint32_t sh2) {
+    // branch-free consume of nb <= 32 bits; `next` is the word after lo, W[qn]. Returns whether a word was taken.
+    __device__ __forceinline__ bool advance(uint32_t nb, uint32_t next) {
+        const uint32_t sh2 = sh + nb;
         const bool need = sh2 >= 32u;
         hi = need ? lo : hi;
-        lo = need ? nxt : lo;
+        lo = need ? next : lo;
         qn += need ? 1u : 0u;
         sh = sh2 & 31u;
+        return need;
     }
     // any other consume: reloads as it goes
     __device__ __forceinline__ void consume_slow(uint32_t nb) {
@@ -438,7 +437,11 @@ __constant__ int8_t k_layout[8][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 
 constexpr uint32_t FULL_MASK = 0xffffffffu;
 
 enum : uint32_t { BUSY_ESCAPE = 2, BUSY_LONG_CODES = 4, BUSY_DEAD = 8, BUSY_PARTIAL = 16 };
-constexpr uint32_t ZRUN_PARKED = 0x40000000u;  // "zero run" of a lane that has nothing (left) to decode
+// pseudo zero runs: a lane in one consumes nothing, like a lane inside a real run (those are < 2^20 long)
+constexpr uint32_t ZRUN_PARKED = 0x40000000u;      // nothing (left) to decode
+constexpr uint32_t ZRUN_REDO = 0x20000000u;        // frozen at a sample that is not decoded yet
+constexpr uint32_t ZRUN_OWES_RUN = 0x10000000u;    // frozen after a decoded sample whose run-length code is not
+constexpr uint32_t ZRUN_FROZEN_MIN = 0x0fff0000u;
 
 // What one lane needs to produce one stream (a channel of a compressed element, or the raw samples of an
 // escape element).
@@ -455,11 +458,75 @@ struct StreamSpec {
     uint32_t u_streams;    // number of U/mono streams that must be finished before the last parked samples are read
 };
 
+// ---- 16 samples without a branch ------------------------------------------------------------------------------
+// Every lane runs the same instructions: one ordinary code (golomb.go:172-201) and -- in the QUIET flavour -- the
+// run-length code that may follow it (dynGet, golomb.go:112-144, :220-245), each committed or not by selects. A lane
+// inside a zero run (clear(predCoefs[count:end]), golomb.go:237) consumes nothing and produces 0. A lane that meets
+// anything else (escape code, packet overrun, a saturating mean, a run that does not fit, a run-length code in the
+// other flavour, ...) FREEZES: it is put into a pseudo zero run whose length counts the samples it sits out, and
+// catches up in the general code after the batch. The QUIET flavour has the longer dependency chain (two codes per
+// sample) and is only used while run-length codes keep appearing; it returns whether this lane saw one.
+template <bool QUIET>
+__device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t &bp, uint32_t pk_size, uint32_t lim,
+                                             uint32_t a0, uint32_t a_last, bool pair, uint32_t a_pair) {
+    bool saw_run = false;
+    uint32_t aj = a0;
+#pragma unroll 2
+    for (uint32_t t = 0; t < CHUNK / 2; t++, aj += 128u) {
+        const uint32_t n0 = br.load(br.qn);  // the word after lo
+        const uint32_t w = br.window();
+        const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
+        const uint32_t k = min(bit_index((e.mean >> 9) + 3u), e.kb);
+        const uint32_t pre1 = pre + 1u;
+        const uint32_t v = __funnelshift_l(shl_go(w, pre1), 0u, k);  // the k bits after the prefix; k == 0 -> 0
+        // prefix * (2^k - 1) + (v >= 2 ? v - 1 : 0): v < 2 means "no suffix value" and gives one bit back
+        const uint32_t r = shl_go(pre, k) - pre1 + max(v, 1u);
+        const uint32_t nb0 = pre + k + (v >= 2u ? 1u : 0u);  // kb <= 22 on this path: <= 31 bits, one refill
+        const bool hold = e.zrun != 0u;
+        const bool take = !hold & (bp < lim) & (pre < 9u) & (r <= 0xffffu);
+        const uint32_t nb = take ? nb0 : 0u;
+        const uint32_t nd = take ? r + e.zmode : 0u;
+        const uint32_t n1 = QUIET ? br.load(br.qn + 1u) : 0u;
+        const bool adv = br.advance(nb, n0);
+        bp += nb;
+        const uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
+        sts32(aj, (int32_t)((nd >> 1) ^ (0u - (nd & 1u))));  // == ((nd+1)>>1) * (1 - 2*(nd&1)) for nd < 2^32-1
+        if (pair) sts32(aj + a_pair, 0);
+        // the run-length code: due after a code that leaves a small mean, unless it was the last sample (golomb.go:220)
+        const bool zdue = take & ((mean2 << 2) < 512u) & (aj != a_last);
+        if (!QUIET) {
+            e.mean = take ? mean2 : e.mean;
+            e.zmode = take ? 0u : e.zmode;
+            e.zrun = zdue ? ZRUN_OWES_RUN : take ? 0u : hold ? e.zrun - 1u : ZRUN_REDO;
+        } else {
+            saw_run |= zdue;
+            int32_t k32 = __clz((int32_t)mean2) - 24 + (int32_t)((mean2 + 16u) >> 6);  // <= 10 when due
+            k32 = max(k32, 0);
+            const uint32_t mz = ((1u << (k32 & 31)) - 1u) & e.wb;
+            const uint32_t w2 = br.window();
+            const uint32_t pre2 = clz_nz(~w2);
+            const uint32_t val = __funnelshift_l(shl_go(w2, pre2 + 1u), 0u, (uint32_t)k32);
+            const uint32_t run = pre2 * mz + max(val, 1u) - 1u;
+            const uint32_t nb2 = pre2 + (uint32_t)k32 + (val >= 2u ? 1u : 0u);  // <= 20 bits
+            // escape-coded runs, a position past the packet and runs past the stream end (golomb.go:232) go the long way
+            const bool go = zdue & (pre2 < 9u) & ((bp >> 3) <= pk_size) & (run <= ((a_last - aj) >> 7));
+            const uint32_t nbb = go ? nb2 : 0u;
+            (void)br.advance(nbb, adv ? n1 : n0);
+            bp += nbb;
+            e.mean = go ? 0u : take ? mean2 : e.mean;
+            e.zmode = go ? 1u : take ? 0u : e.zmode;
+            e.zrun = go ? run : zdue ? ZRUN_OWES_RUN : take ? 0u : hold ? e.zrun - 1u : ZRUN_REDO;
+        }
+    }
+    return saw_run;
+}
+
 // Produce one stream for consumer `cons`: ceil(nmax/32) ring slots (at least one: it carries the job).
 // For an interleaved escape pair both consumers' slots are filled in the same pass.
 __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int cons, uint32_t *seq, const Packet &pk,
                                                const DevConfig &cfg, BitReader &br, uint32_t &bp, int32_t &st,
-                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, RoleTimer &rt) {
+                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, bool &quiet,
+                                               RoleTimer &rt) {
     bool active = sp.active && st == ST_OK;
     const uint32_t nmax = __reduce_max_sync(FULL_MASK, active ? sp.n : 0u);
     const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
@@ -507,9 +574,12 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
         const uint32_t base_i = c * CHUNK;
         const uint32_t cnt = (active && sp.n > base_i) ? min((uint32_t)CHUNK, sp.n - base_i) : 0u;
         const uint32_t a_last = a_dst + (sp.n - 1u - base_i) * 128u;  // ring address of the stream's last sample, if it is in this chunk
-        // a lane with a short last chunk stops in the middle of it: the warp takes the general step for this chunk
+        // a lane with a short last chunk stops in the middle of it: it takes the general step for this chunk
         busy = (busy & ~BUSY_PARTIAL) | ((cnt != 0u && cnt != (uint32_t)CHUNK) ? BUSY_PARTIAL : 0u);
         if (cnt == 0u) e.zrun = ZRUN_PARKED;  // nothing (left) to decode: idle without touching bp
+        // a lane that cannot use the straight-line decode at all (escape element, long codes, short chunk) fails
+        // the packet-overrun test of every sample instead
+        const uint32_t lim = busy ? 0u : e.size8;
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; half++) {
             // keep the staged window ahead of the reader: 16 samples eat at most 16 x 67 bits = 9 chunks of 16
@@ -519,102 +589,46 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                 br.top_up();
                 rt.add(2, tt);
             }
-            // The hot loop below is straight-line for the whole warp; it is left (uniformly) for the general step of one
-            // sample, or for run-length codes the straight-line form does not cover, and entered again.
-            // the loop counter is the shared-memory address of the lane's ring entry: sample j lives at a_dst + 128 j
-            uint32_t aj = a_dst + half * (CHUNK / 2) * 128u;
-            const uint32_t a_end = aj + (CHUNK / 2) * 128u;
+            // 16 samples without a branch (decode_batch), in the flavour the previous batches call for
+            const uint32_t a0 = a_dst + half * (CHUNK / 2) * 128u;  // ring address of the lane's sample: a_dst + 128 j
+            if (quiet) {
+                const bool saw_run = decode_batch<true>(br, e, bp, pk.size, lim, a0, a_last, pair, a_pair);
+                quiet = __any_sync(FULL_MASK, saw_run);
+            } else {
+                (void)decode_batch<false>(br, e, bp, pk.size, lim, a0, a_last, pair, a_pair);
+            }
+            // ---- frozen lanes catch up: general step (DynDecomp as written) for the samples they sat out ------------
+            const bool frozen = e.zrun >= ZRUN_FROZEN_MIN && e.zrun < ZRUN_PARKED - 0x10000u;
+            if (__any_sync(FULL_MASK, frozen)) {
+                // run-length codes have started to appear: the next batch decodes them in line
+                quiet = quiet | __any_sync(FULL_MASK, frozen && e.zrun <= ZRUN_OWES_RUN);
+                if (frozen) {
+                    const bool owes = e.zrun <= ZRUN_OWES_RUN;
+                    const uint32_t since = (owes ? ZRUN_OWES_RUN : ZRUN_REDO) - e.zrun;  // samples after the one it froze at
+                    const uint32_t jend = (half + 1u) * (CHUNK / 2);
+                    uint32_t j = jend - 1u - since;
+                    e.zrun = 0;
+                    bool alive = true;
+                    if (owes) {  // sample j is decoded, its run-length code is not
+                        alive = zero_run_start(pk, br, bp, e, base_i + j, sp.n, st);
+                        j++;
+                    }
 #pragma unroll 1
-            while (aj != a_end) {
-                uint32_t left = 0;  // 1: sample j needs the general step; 2: lanes in `pend` owe a run-length code
-                bool pend = false;
-#pragma unroll 2
-                for (; aj != a_end; aj += 128u) {
-                    br.begin_sample();
-                    // ---- one ordinary code (golomb.go:172-201), decoded by every lane whether it wants it or not ----
-                    const uint32_t w = br.window();
-                    const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
-                    const uint32_t k = min(bit_index((e.mean >> 9) + 3u), e.kb);
-                    const uint32_t pre1 = pre + 1u;
-                    const uint32_t v = __funnelshift_l(shl_go(w, pre1), 0u, k);  // the k bits after the prefix; k == 0 -> 0
-                    // prefix * (2^k - 1) + (v >= 2 ? v - 1 : 0): v < 2 means "no suffix value" and gives one bit back
-                    const uint32_t r = shl_go(pre, k) - pre1 + max(v, 1u);
-                    const uint32_t nb0 = pre + k + (v >= 2u ? 1u : 0u);
-                    // A lane inside a zero run (clear(predCoefs[count:end]), golomb.go:237) -- or parked in an endless
-                    // one because it has nothing left to decode -- consumes nothing and produces 0 with the same
-                    // instructions. Anything else (escape code, escape element, packet overrun, a saturating mean,
-                    // cookies whose codes can exceed one refill, a short last chunk) sends the WARP to the general step.
-                    const bool inrun = e.zrun != 0u;
-                    const bool ok = inrun | ((busy == 0u) & (pre < 9u) & (bp < e.size8) & (r <= 0xffffu));
-                    if (!__all_sync(FULL_MASK, ok)) {
-                        left = 1;
-                        break;
-                    }
-                    const uint32_t nb = inrun ? 0u : nb0;  // kb <= 22 here: nb <= 31, one refill at most
-                    const uint32_t nd = inrun ? 0u : r + e.zmode;
-                    br.commit(br.sh + nb);
-                    bp += nb;
-                    const uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
-                    e.mean = mean2;
-                    e.zmode = inrun ? e.zmode : 0u;
-                    e.zrun = inrun ? e.zrun - 1u : 0u;
-                    sts32(aj, (int32_t)((nd >> 1) ^ (0u - (nd & 1u))));  // == ((nd+1)>>1) * (1 - 2*(nd&1)) for nd < 2^32-1
-                    if (pair) sts32(aj + a_pair, 0);
-                    const bool zdue = !inrun & ((mean2 << 2) < 512u) & (aj != a_last);  // golomb.go:220
-                    if (__any_sync(FULL_MASK, zdue)) {
-                        // the run-length code that follows (dynGet, golomb.go:112-144, :220-245), branch-free
-                        int32_t k32 = __clz((int32_t)mean2) - 24 + (int32_t)((mean2 + 16u) >> 6);
-                        k32 = max(k32, 0);
-                        pend = zdue & ((k32 > 16) | ((bp >> 3) > pk.size));  // never for a sane mean / position
-                        const bool go = zdue & !pend;
-                        const uint32_t nxt2 = br.load(br.qn);  // the word after lo, should the first code have refilled
-                        const uint32_t mz = ((1u << (k32 & 31)) - 1u) & e.wb;
-                        const uint32_t w2 = br.window();
-                        const uint32_t pre2 = clz_nz(~w2);
-                        const bool esc2 = pre2 >= 9u;
-                        const uint32_t val = __funnelshift_l(shl_go(w2, pre2 + 1u), 0u, (uint32_t)k32);
-                        const bool big2 = val >= 2u;
-                        const uint32_t run = esc2 ? ((w2 << 9) >> 16) : pre2 * mz + (big2 ? val - 1u : 0u);
-                        const uint32_t nb2 = esc2 ? 25u : pre2 + (uint32_t)k32 + (big2 ? 1u : 0u);
-                        br.nxt = nxt2;
-                        br.commit(br.sh + (go ? nb2 : 0u));  // nb2 <= 26: one refill at most
-                        bp += go ? nb2 : 0u;
-                        const bool over = go & (run > ((a_last - aj) >> 7));  // i + 1 + run > n, golomb.go:232-234
-                        e.zrun = over ? ZRUN_PARKED : go ? run : e.zrun;
-                        e.zmode = go ? (run >= 65535u ? 0u : 1u) : e.zmode;
-                        e.mean = go ? 0u : e.mean;
-                        st = over ? (int32_t)ST_SAMPLE_OVERRUN : st;
-                        active = active & !over;
-                        busy |= over ? (uint32_t)BUSY_DEAD : 0u;
-                        if (__any_sync(FULL_MASK, pend)) {
-                            left = 2;
-                            aj += 128u;
-                            break;
+                    for (; j < jend; j++) {
+                        int32_t res = 0, res2 = 0;
+                        if (alive && j < cnt) {
+                            if (sp.escape) {
+                                res = escape_sample(br, sp.chan_bits);
+                                if (pair) res2 = escape_sample(br, sp.chan_bits);
+                            } else if (!entropy_next(pk, br, bp, e, base_i + j, sp.n, res, st)) {
+                                alive = false;
+                                res = 0;
+                            }
                         }
+                        sts32(a_dst + j * 128u, res);
+                        if (pair) sts32(a_dst + j * 128u + a_pair, res2);
                     }
-                }
-                const uint32_t j = (aj - a_dst) >> 7;
-                if (left == 1) {
-                    const uint32_t i = base_i + j;
-                    int32_t res = 0, res2 = 0;
-                    if (j < cnt && !(busy & BUSY_DEAD)) {
-                        if (e.zrun > 0u && (busy & ~BUSY_PARTIAL) == 0u) {  // inside a zero run
-                            e.zrun--;
-                        } else if (sp.escape) {
-                            res = escape_sample(br, sp.chan_bits);
-                            if (pair) res2 = escape_sample(br, sp.chan_bits);
-                        } else if (!entropy_next(pk, br, bp, e, i, sp.n, res, st)) {
-                            active = false;
-                            busy |= BUSY_DEAD;  // a failed lane idles through the rest of the stream
-                            e.zrun = ZRUN_PARKED;
-                            res = 0;
-                        }
-                    }
-                    sts32(aj, res);
-                    if (pair) sts32(aj + a_pair, res2);
-                    aj += 128u;
-                } else if (left == 2) {
-                    if (pend && !zero_run_start(pk, br, bp, e, base_i + j - 1u, sp.n, st)) {
+                    if (!alive) {  // a failed lane idles through the rest of the stream
                         active = false;
                         busy |= BUSY_DEAD;
                         e.zrun = ZRUN_PARKED;
@@ -766,6 +780,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     if (valid && pk.size > 0x0FFFFFFFu) { st = ST_REF_PANIC; parsing = false; }  // bit positions are 32-bit here
     uint32_t seq[2] = {0, 0};
     uint32_t nstreams0 = 0;  // streams handed to the U/mono predictor warp so far
+    bool quiet = false;      // warp-uniform: run-length codes keep appearing, decode them in line (decode_batch<true>)
     BitReader br;
     br.fifo = fifo_addr;
     RoleTimer rt(lane, 0);
@@ -838,7 +853,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                 a.shift_bitpos = h.shift_bitpos;
                 a.u_streams = nstreams0;
             }
-            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, rt);
+            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, quiet, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
                 if ((st & 0xff) == ST_REF_PANIC) st |= ctx;
                 else st |= ctx | ((pass == 1 ? ENT_V : h.stereo ? ENT_U : ENT_MONO) << 12);
