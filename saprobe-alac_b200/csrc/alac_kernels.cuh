@@ -300,6 +300,11 @@ struct BitReader {
     }
 };
 
+// The ring carries residuals as the sign-folded codes the entropy stage decodes (golomb.go:207-214: odd -> negative),
+// so the fold is undone by the predictor warps, which have the time.
+__device__ __forceinline__ int32_t code_to_residual(uint32_t nd) { return (int32_t)((nd >> 1) ^ (0u - (nd & 1u))); }
+__device__ __forceinline__ int32_t residual_to_code(int32_t r) { return (int32_t)(((uint32_t)r << 1) ^ (uint32_t)(r >> 31)); }
+
 // ---- adaptive Golomb-Rice state (DynDecomp, golomb.go:148-253) --------------------------------------
 struct Entropy {
     uint32_t mean, zmode, zrun;
@@ -468,11 +473,11 @@ struct StreamSpec {
 // sample) and is only used while run-length codes keep appearing; it returns whether this lane saw one.
 template <bool QUIET>
 __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t &bp, uint32_t pk_size, uint32_t lim,
-                                             uint32_t a0, uint32_t a_last, bool pair, uint32_t a_pair) {
+                                             uint32_t a0, uint32_t a_last) {
     bool saw_run = false;
-    uint32_t aj = a0;
+    const uint32_t a_end = a0 + (CHUNK / 2) * 128u;
 #pragma unroll 2
-    for (uint32_t t = 0; t < CHUNK / 2; t++, aj += 128u) {
+    for (uint32_t aj = a0; aj != a_end; aj += 128u) {
         const uint32_t n0 = br.load(br.qn);  // the word after lo
         const uint32_t w = br.window();
         const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
@@ -481,7 +486,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
         const uint32_t v = __funnelshift_l(shl_go(w, pre1), 0u, k);  // the k bits after the prefix; k == 0 -> 0
         // prefix * (2^k - 1) + (v >= 2 ? v - 1 : 0): v < 2 means "no suffix value" and gives one bit back
         const uint32_t r = shl_go(pre, k) - pre1 + max(v, 1u);
-        const uint32_t nb0 = pre + k + (v >= 2u ? 1u : 0u);  // kb <= 22 on this path: <= 31 bits, one refill
+        const uint32_t nb0 = pre + k + (min(v, 2u) >> 1);  // kb <= 22 on this path: <= 31 bits, one refill
         const bool hold = e.zrun != 0u;
         const bool take = !hold & (bp < lim) & (pre < 9u) & (r <= 0xffffu);
         const uint32_t nb = take ? nb0 : 0u;
@@ -490,14 +495,15 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
         const bool adv = br.advance(nb, n0);
         bp += nb;
         const uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
-        sts32(aj, (int32_t)((nd >> 1) ^ (0u - (nd & 1u))));  // == ((nd+1)>>1) * (1 - 2*(nd&1)) for nd < 2^32-1
-        if (pair) sts32(aj + a_pair, 0);
+        sts32(aj, (int32_t)nd);  // the consumer undoes the sign fold (code_to_residual)
         // the run-length code: due after a code that leaves a small mean, unless it was the last sample (golomb.go:220)
         const bool zdue = take & ((mean2 << 2) < 512u) & (aj != a_last);
+        // a real or pseudo zero run loses one sample; a lane that is not in one and did not take its code freezes
+        uint32_t z = (max(e.zrun, 1u) - 1u) | ((!hold & !take) ? ZRUN_REDO : 0u);
         if (!QUIET) {
             e.mean = take ? mean2 : e.mean;
             e.zmode = take ? 0u : e.zmode;
-            e.zrun = zdue ? ZRUN_OWES_RUN : take ? 0u : hold ? e.zrun - 1u : ZRUN_REDO;
+            e.zrun = z | (zdue ? ZRUN_OWES_RUN : 0u);
         } else {
             saw_run |= zdue;
             int32_t k32 = __clz((int32_t)mean2) - 24 + (int32_t)((mean2 + 16u) >> 6);  // <= 10 when due
@@ -507,7 +513,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
             const uint32_t pre2 = clz_nz(~w2);
             const uint32_t val = __funnelshift_l(shl_go(w2, pre2 + 1u), 0u, (uint32_t)k32);
             const uint32_t run = pre2 * mz + max(val, 1u) - 1u;
-            const uint32_t nb2 = pre2 + (uint32_t)k32 + (val >= 2u ? 1u : 0u);  // <= 20 bits
+            const uint32_t nb2 = pre2 + (uint32_t)k32 + (min(val, 2u) >> 1);  // <= 20 bits
             // escape-coded runs, a position past the packet and runs past the stream end (golomb.go:232) go the long way
             const bool go = zdue & (pre2 < 9u) & ((bp >> 3) <= pk_size) & (run <= ((a_last - aj) >> 7));
             const uint32_t nbb = go ? nb2 : 0u;
@@ -515,7 +521,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
             bp += nbb;
             e.mean = go ? 0u : take ? mean2 : e.mean;
             e.zmode = go ? 1u : take ? 0u : e.zmode;
-            e.zrun = go ? run : zdue ? ZRUN_OWES_RUN : take ? 0u : hold ? e.zrun - 1u : ZRUN_REDO;
+            e.zrun = z | (go ? run : zdue ? ZRUN_OWES_RUN : 0u);
         }
     }
     return saw_run;
@@ -592,10 +598,10 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
             // 16 samples without a branch (decode_batch), in the flavour the previous batches call for
             const uint32_t a0 = a_dst + half * (CHUNK / 2) * 128u;  // ring address of the lane's sample: a_dst + 128 j
             if (quiet) {
-                const bool saw_run = decode_batch<true>(br, e, bp, pk.size, lim, a0, a_last, pair, a_pair);
+                const bool saw_run = decode_batch<true>(br, e, bp, pk.size, lim, a0, a_last);
                 quiet = __any_sync(FULL_MASK, saw_run);
             } else {
-                (void)decode_batch<false>(br, e, bp, pk.size, lim, a0, a_last, pair, a_pair);
+                (void)decode_batch<false>(br, e, bp, pk.size, lim, a0, a_last);
             }
             // ---- frozen lanes catch up: general step (DynDecomp as written) for the samples they sat out ------------
             const bool frozen = e.zrun >= ZRUN_FROZEN_MIN && e.zrun < ZRUN_PARKED - 0x10000u;
@@ -625,8 +631,8 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                                 res = 0;
                             }
                         }
-                        sts32(a_dst + j * 128u, res);
-                        if (pair) sts32(a_dst + j * 128u + a_pair, res2);
+                        sts32(a_dst + j * 128u, residual_to_code(res));
+                        if (pair) sts32(a_dst + j * 128u + a_pair, residual_to_code(res2));
                     }
                     if (!alive) {  // a failed lane idles through the rest of the stream
                         active = false;
@@ -1240,9 +1246,8 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
     const int32_t order = (int32_t)jb.order;
-    // live emission (2-channel streams): the decoded V samples replace the residuals in the ring slot, the emit
-    // warp takes them from there; decided per stream, uniform over the warp
-    constexpr bool live_any = LIVE;
+    // LIVE (2-channel streams, V): the decoded samples replace the residuals in the ring slot and the emit warp takes
+    // them from there; otherwise they are parked in the scratch.
     const bool fir_order = order == 4 || order == 5 || order == 6 || order == 8;
     const uint32_t fir_from = fir_order ? (uint32_t)order + 1u : 0xffffffffu;
     const bool copy = order == 0;  // order 0 copies; warm-up and order 31 accumulate
@@ -1277,7 +1282,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 #pragma unroll 2
         for (uint32_t j = 0; j < CHUNK; j++) {
             const uint32_t i = ck * CHUNK + j;
-            int32_t r = src[j * 32];
+            int32_t r = code_to_residual((uint32_t)src[j * 32]);
             if (MODE) {  // order-31 pre-pass on the residuals (decoder.go:306-308)
                 const int32_t dn = (i == 0) ? r : sext_go(r + dprev, cs);
                 r = mode ? dn : r;
@@ -1319,7 +1324,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 #pragma unroll
             for (int t = T; t > 0; t--) h[t] = h[t - 1];
             h[0] = x;
-            if (live_any) vdst[j * 32] = x;
+            if (LIVE) vdst[j * 32] = x;
             else if (i < n_lane) *outp = x;
             outp += 32;
         }
@@ -1360,7 +1365,7 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
 #pragma unroll 1
         for (uint32_t j = 0; j < CHUNK; j++) {
             const uint32_t i = ck * CHUNK + j;
-            int32_t r = src[j * 32];
+            int32_t r = code_to_residual((uint32_t)src[j * 32]);
             if (active && i < jb.n) {
                 r = delta_step(mode, dprev, r, i, cs);
                 int32_t x;
