@@ -186,21 +186,25 @@ constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged pe
 constexpr int LIVE_SHIFT_CHUNKS = 10;  // 16-byte chunks covering 32 frames x 2 channels x 2 shift bytes at any alignment
 
 struct DecShared {
-    // barriers first: stage 3 reuses everything behind them as its transpose tiles
+    // Compressed bytes staged by cp.async: a 512-byte window per lane, [lane][chunk ^ (lane & 7)]. The window of a lane
+    // starts on a 512-byte boundary of the shared address space (the struct sits at a 1024-byte aligned base), so the
+    // address of a word is one LOP3: (byte offset & 0x1fc) ^ window base; the XOR spreads the lanes over the banks.
+    uint4 fifo[32][FIFO_CHUNKS];
+    int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (16 KB)
+    uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
+                                             // live-emit word, shift bit position, U streams to wait for
+    // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
+    int32_t live_u[CHUNK][32];
+    uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
+    // barriers last: stage 3 reuses everything in front of them as its transpose tiles
     uint64_t full_bar[2][RING_SLOTS];
     uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
     uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
     volatile uint32_t u_streams_done;   // streams the U/mono predictor warp has finished (release/acquire by fences)
-    uint32_t pad_[27];                  // keeps `ring` 16-byte aligned: 160 + 4 + 108 = 272
-    int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (32 KB)
-    uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
-                                             // live-emit word, shift bit position, U streams to wait for
-    uint4 fifo[32][FIFO_CHUNKS + 1];         // compressed bytes staged by cp.async, [lane][chunk] (+1: bank skew)
-    // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
-    int32_t live_u[CHUNK][32];
-    uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
+    uint32_t rotation;                  // role rotation of this CTA
 };
-static_assert(offsetof(DecShared, ring) % 16 == 0, "ring must be 16-byte aligned");
+static_assert(offsetof(DecShared, fifo) == 0 && FIFO_CHUNKS * 16 == 512, "lane windows must be 512-byte aligned");
+static_assert(offsetof(DecShared, ring) % 16 == 0 && offsetof(DecShared, live_shift) % 16 == 0 && offsetof(DecShared, full_bar) % 8 == 0, "alignment");
 
 
 // job meta word
@@ -214,7 +218,6 @@ __device__ __forceinline__ uint32_t job_meta(uint32_t kind, uint32_t order, uint
 // The compressed packet is staged into shared memory with 128-bit cp.async (zero-filled past the packet
 // end = the reference's zero padding, bitbuffer.go:36-51) at least one half-chunk period ahead of its use;
 // the hot loop then needs one LDS per sample, issued at the top of the iteration, and a branch-free refill.
-constexpr uint32_t FIFO_LANE_BYTES = FIFO_CHUNKS * 16 + 16;  // 528: +16 skews the lanes over the banks
 
 // clz(x) for x != 0 in ONE instruction (FLO.U32.SH); 0xffffffff for x == 0
 __device__ __forceinline__ uint32_t clz_nz(uint32_t x) {
@@ -233,9 +236,9 @@ __device__ __forceinline__ uint32_t bit_index(uint32_t x) {
 struct BitReader {
     const uint8_t *gbase;  // 16-byte aligned global address at or below the packet start
     uint32_t end_rel;      // packet end, bytes from gbase
-    uint32_t fifo;         // shared address of this lane's window (FIFO_CHUNKS x 16 bytes)
+    uint32_t fifo;         // shared address of this lane's window, XORed with the lane's bank swizzle
     uint32_t req;          // next 16-byte chunk to request
-    uint32_t qn;           // index (32-bit words from gbase) of the next word to load; hi = qn-2, lo = qn-1
+    uint32_t qo;           // byte offset from gbase (multiple of 4) of the next word to load; hi, lo are the two before it
     uint32_t hi, lo;       // big-endian-converted words
     uint32_t sh;           // bits of hi already consumed (0..31)
 
@@ -243,12 +246,13 @@ struct BitReader {
         const uint32_t b0 = c << 4;
         const uint32_t nbytes = b0 >= end_rel ? 0u : min(16u, end_rel - b0);
         const uint8_t *src = gbase + (nbytes ? b0 : 0u);
-        const uint32_t dst = fifo + ((c & (FIFO_CHUNKS - 1)) << 4);
+        const uint32_t dst = fifo ^ (b0 & (FIFO_CHUNKS * 16 - 16));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
     }
     __device__ __forceinline__ static void wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-    __device__ __forceinline__ uint32_t load(uint32_t widx) const {
-        const uint32_t a = fifo + ((widx & (FIFO_CHUNKS * 4 - 1)) << 2);
+    // the word at byte offset `off` (multiple of 4) from gbase
+    __device__ __forceinline__ uint32_t load(uint32_t off) const {
+        const uint32_t a = (off & (FIFO_CHUNKS * 16 - 4)) ^ fifo;
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
         return __byte_perm(v, 0, 0x0123);
@@ -256,7 +260,7 @@ struct BitReader {
     // land what was requested a period ago, request up to a full window ahead of the reader
     __device__ __forceinline__ void top_up() {
         wait_all();
-        const uint32_t lim = (qn >> 2) + FIFO_CHUNKS;
+        const uint32_t lim = (qo >> 4) + FIFO_CHUNKS;
         while (req < lim) request(req++);
     }
     __device__ __forceinline__ void init(const Packet &pk, uint32_t bp, uint32_t fifo_addr) {
@@ -266,25 +270,25 @@ struct BitReader {
         end_rel = mis + pk.size;
         fifo = fifo_addr;
         const uint32_t abp = bp + mis * 8u;
-        const uint32_t q = abp >> 5;
+        const uint32_t q = (abp >> 5) << 2;
         sh = abp & 31u;
         wait_all();  // nothing of a previous element may still be landing in the window
-        req = q >> 2;
+        req = q >> 4;
         const uint32_t lim = req + FIFO_CHUNKS;
         while (req < lim) request(req++);
         wait_all();
         hi = load(q);
-        lo = load(q + 1u);
-        qn = q + 2u;
+        lo = load(q + 4u);
+        qo = q + 8u;
     }
     __device__ __forceinline__ uint32_t window() const { return __funnelshift_l(lo, hi, sh); }
-    // branch-free consume of nb <= 32 bits; `next` is the word after lo, W[qn]. Returns whether a word was taken.
+    // branch-free consume of nb <= 32 bits; `next` is the word after lo. Returns whether a word was taken.
     __device__ __forceinline__ bool advance(uint32_t nb, uint32_t next) {
         const uint32_t sh2 = sh + nb;
         const bool need = sh2 >= 32u;
         hi = need ? lo : hi;
         lo = need ? next : lo;
-        qn += need ? 1u : 0u;
+        if (need) qo += 4u;
         sh = sh2 & 31u;
         return need;
     }
@@ -293,8 +297,8 @@ struct BitReader {
         sh += nb;
         while (sh >= 32u) {
             hi = lo;
-            lo = load(qn);
-            qn += 1u;
+            lo = load(qo);
+            qo += 4u;
             sh -= 32u;
         }
     }
@@ -478,7 +482,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
     const uint32_t a_end = a0 + (CHUNK / 2) * 128u;
 #pragma unroll 2
     for (uint32_t aj = a0; aj != a_end; aj += 128u) {
-        const uint32_t n0 = br.load(br.qn);  // the word after lo
+        const uint32_t n0 = br.load(br.qo);  // the word after lo
         const uint32_t w = br.window();
         const uint32_t pre = clz_nz(~w);  // leading ones; 0xffffffff when all 32 are ones
         const uint32_t k = min(bit_index((e.mean >> 9) + 3u), e.kb);
@@ -491,7 +495,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
         const bool take = !hold & (bp < lim) & (pre < 9u) & (r <= 0xffffu);
         const uint32_t nb = take ? nb0 : 0u;
         const uint32_t nd = take ? r + e.zmode : 0u;
-        const uint32_t n1 = QUIET ? br.load(br.qn + 1u) : 0u;
+        const uint32_t n1 = QUIET ? br.load(br.qo + 4u) : 0u;
         const bool adv = br.advance(nb, n0);
         bp += nb;
         const uint32_t mean2 = e.pb * nd + e.mean - ((e.pb * e.mean) >> 9);
@@ -499,11 +503,12 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
         // the run-length code: due after a code that leaves a small mean, unless it was the last sample (golomb.go:220)
         const bool zdue = take & ((mean2 << 2) < 512u) & (aj != a_last);
         // a real or pseudo zero run loses one sample; a lane that is not in one and did not take its code freezes
-        uint32_t z = (max(e.zrun, 1u) - 1u) | ((!hold & !take) ? ZRUN_REDO : 0u);
+        if (hold) e.zrun -= 1u;
+        if (!hold & !take) e.zrun = ZRUN_REDO;
         if (!QUIET) {
             e.mean = take ? mean2 : e.mean;
             e.zmode = take ? 0u : e.zmode;
-            e.zrun = z | (zdue ? ZRUN_OWES_RUN : 0u);
+            if (zdue) e.zrun = ZRUN_OWES_RUN;
         } else {
             saw_run |= zdue;
             int32_t k32 = __clz((int32_t)mean2) - 24 + (int32_t)((mean2 + 16u) >> 6);  // <= 10 when due
@@ -521,7 +526,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
             bp += nbb;
             e.mean = go ? 0u : take ? mean2 : e.mean;
             e.zmode = go ? 1u : take ? 0u : e.zmode;
-            e.zrun = z | (go ? run : zdue ? ZRUN_OWES_RUN : 0u);
+            if (zdue) e.zrun = go ? run : ZRUN_OWES_RUN;
         }
     }
     return saw_run;
@@ -777,7 +782,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     PacketDesc *desc = descs + pidx;
-    const uint32_t fifo_addr = smem_u32(&sm.fifo[lane][0]);
+    const uint32_t fifo_addr = smem_u32(&sm.fifo[lane][0]) ^ ((lane & 7u) << 4);
 
     Cursor cur{0, false};
     uint32_t ns = cfg.frame_length, chan_idx = 0, nops = 0;
@@ -1902,9 +1907,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
                                                                      uint8_t *__restrict__ pcm_out, uint64_t out_stride,
                                                                      uint32_t *__restrict__ out_bytes,
                                                                      int32_t *__restrict__ status) {
-    extern __shared__ __align__(16) uint8_t dec_smem[];
+    extern __shared__ __align__(1024) uint8_t dec_smem[];
     DecShared &sm = *reinterpret_cast<DecShared *>(dec_smem);
-    __shared__ uint32_t s_rotation;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int c = 0; c < 2; c++)
@@ -1919,21 +1923,20 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
         // of co-resident CTAs on different schedulers
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        s_rotation = atomicAdd(&g_sm_ticket[smid & 255u], 1u);
+        sm.rotation = atomicAdd(&g_sm_ticket[smid & 255u], 1u);
     }
     __syncthreads();
     // rotate the roles over the warp slots so co-resident CTAs do not stack their entropy warps on one SMSP
-    const uint32_t role = (warp + s_rotation) % 4u;
+    const uint32_t role = (warp + sm.rotation) % 4u;
     if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
     else if (role == 3) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
     else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
     __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
-    // stage 3 reuses the ring / job / window memory as its transpose tile
+    // stage 3 reuses the window / ring / job memory as its transpose tile
     EmitArgs ea{packed, offsets, sizes, npackets, scratch, descs, pcm_out, out_stride};
     RoleTimer rt(lane, 8 + (int)(warp % 3u));
     const unsigned long long t_emit = rt.now();
-    emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem + offsetof(DecShared, ring),
-                                 (uint32_t)(sizeof(DecShared) - offsetof(DecShared, ring)));
+    emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
     rt.add(0, t_emit);
     rt.flush(1);
 }
