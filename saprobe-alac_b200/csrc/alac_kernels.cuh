@@ -1,21 +1,23 @@
-// alac_kernels.cuh -- hand-written sm_100a kernels for the ALAC packet-decode hot path.
+// alac_kernels.cuh -- the hand-written sm_100a kernel of the ALAC packet-decode hot path.
 //
-// Two kernels, both parallel ACROSS packets (packets are independent, decoder.go:79-87):
+// One kernel, alac_decode_kernel, parallel ACROSS packets (packets are independent, decoder.go:79-87) and across
+// STAGES. One CTA = 32 packets, four role warps with lane = packet:
 //
-//   alac_decode_kernel  stage 1+2. One CTA = 32 packets, three role warps with lane = packet: an ENTROPY
-//                       warp walks the element grammar of decodePacketInto (decoder.go:133-207) and
-//                       the adaptive Golomb-Rice stream (DynDecomp, golomb.go:148-253) and hands
-//                       residuals through a shared-memory ring (mbarrier full/empty pairs) to two
-//                       PREDICTOR warps running the sign-LMS filter (UnpcBlock, predictor.go:45-684),
-//                       one for the mono/U stream and one for the V stream of every element, so the
-//                       serial entropy chain of a packet overlaps both predictor chains. Compressed
-//                       bytes are staged into shared memory with 128-bit cp.async (zero-fill past the
-//                       packet end) one period ahead of their use. Decoded channel samples are parked
-//                       as int32 in a lane-interleaved scratch ([group][slot][sample][32 lanes]) so
-//                       every warp store is one 128-byte line.
-//   alac_emit_kernel    stage 3. Fully data-parallel un-mix + shift-merge + interleaved little-endian
-//                       PCM emit (WriteStereo*/WriteMono*, matrix.go:30-301) through a shared-memory
-//                       transpose so global stores are coalesced / 128-bit.
+//   ENTROPY     walks the element grammar of decodePacketInto (decoder.go:133-207) and the adaptive Golomb-Rice
+//               stream (DynDecomp, golomb.go:148-253) in branch-free batches of 16 samples (decode_batch) and hands
+//               the codes through shared-memory rings (mbarrier full/empty pairs) to the predictor warps. Compressed
+//               bytes are staged into shared memory with 128-bit cp.async (zero-fill past the packet end) one
+//               period ahead of their use.
+//   PREDICTOR 0 sign-LMS filter (UnpcBlock, predictor.go:45-684) of the mono / U stream of every element; parks the
+//               decoded samples as int32 in a lane-interleaved scratch ([group][slot][sample][32 lanes]: every warp
+//               store is one 128-byte line).
+//   PREDICTOR 1 the same for the V stream, so the serial entropy chain of a packet overlaps both predictor chains.
+//               For 2-channel streams it writes V back into the ring slot instead of parking it.
+//   EMIT        (2-channel streams) un-mix + shift-merge + interleaved little-endian PCM (WriteStereo*, matrix.go:30-215)
+//               of every finished ring slot, 128-bit stores to the packet's own output slot.
+//
+// Whatever is not emitted live (mono, multi-channel, escape pairs, short or failed packets) is written by the whole
+// CTA after the role warps are done, from the parked samples (emit_group: WriteStereo*/WriteMono*, matrix.go:30-301).
 //
 // Integer semantics are the Go reference's: wrap-around int32/uint32, shifts >= 32 give 0 / sign
 // fill (PTX shl/shr clamp exactly like that), int32 coefficients for orders 4/5/6/8 and int16-wrapping
@@ -175,10 +177,9 @@ struct RoleTimer {
 };
 
 // ---- geometry of one decode CTA ---------------------------------------------------------------------
-// 3 warps, 32 packets: one ENTROPY warp (lane = packet) walks the grammar and the Golomb stream and hands
-// residuals, 32 samples at a time, through a shared-memory ring to two PREDICTOR warps (lane = packet):
-// consumer 0 takes the mono / U stream of every element, consumer 1 the V stream. The serial entropy chain
-// of a packet (U then V, golomb.go) therefore overlaps with both predictor chains.
+// 4 warps, 32 packets: the ENTROPY warp hands residual codes, 32 samples at a time, through a shared-memory ring to
+// two PREDICTOR warps: consumer 0 takes the mono / U stream of every element, consumer 1 the V stream; the EMIT warp
+// follows consumer 1's ring.
 constexpr int DEC_THREADS = 128;
 constexpr int RING_SLOTS = 2;    // ring depth per consumer
 constexpr int CHUNK = 32;        // samples per ring slot
