@@ -162,7 +162,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
 // Optional role timing (clock64 per role, lane 0): [cta][16] (8..10 = emit tail per warp), E total, E wait-empty, E top-up, P0 total, P0 wait,
 // P1 total, P1 wait, unused. Enabled by pointing g_role_cycles at a buffer (alacb200_debug_role_cycles).
 __device__ unsigned long long *g_role_cycles = nullptr;
-__device__ unsigned int g_sm_ticket[256];  // per-SM CTA counter (monotonic; only its value mod 4 is used)
+__device__ unsigned int g_sm_ticket[256];        // per-SM CTA counter (monotonic; only its value mod 4 is used)
+__device__ unsigned int g_sm_entropy_load[256];  // per SM: four 8-bit counts of resident entropy warps, by sub-partition
 __device__ unsigned int g_debug_flags = 0;  // bit 0: no live emission (developer experiments)
 struct RoleTimer {
     unsigned long long *slot;
@@ -202,7 +203,8 @@ struct DecShared {
     uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
     uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
     volatile uint32_t u_streams_done;   // streams the U/mono predictor warp has finished (release/acquire by fences)
-    uint32_t rotation;                  // role rotation of this CTA
+    uint32_t rotation;                  // sub-partition chosen for the entropy warp of this CTA
+    uint32_t subpart_mask;              // sub-partitions the four warps report
 };
 static_assert(offsetof(DecShared, fifo) == 0 && FIFO_CHUNKS * 16 == 512, "lane windows must be 512-byte aligned");
 static_assert(offsetof(DecShared, ring) % 16 == 0 && offsetof(DecShared, live_shift) % 16 == 0 && offsetof(DecShared, full_bar) % 8 == 0, "alignment");
@@ -1919,20 +1921,53 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
             }
         for (int s = 0; s < RING_SLOTS; s++) mbar_init(&sm.vdone_bar[s], 32);
         sm.u_streams_done = 0;
-        // CTAs that share an SM take consecutive tickets, whatever their block indices are: the hardware gives the
-        // four warps of a CTA to the four sub-partitions in order, so consecutive rotations keep e.g. the entropy warps
-        // of co-resident CTAs on different schedulers
+        // The hardware puts the four warps of a CTA on the four SM sub-partitions (one each, starting anywhere), and the
+        // entropy warp is the one that must not share a scheduler with another entropy warp. Per SM, a packed word
+        // counts the resident entropy warps of every sub-partition; the CTA puts its own on the least loaded one.
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        sm.rotation = atomicAdd(&g_sm_ticket[smid & 255u], 1u);
+        unsigned int *word = &g_sm_entropy_load[smid & 255u];
+        const uint32_t first = atomicAdd(&g_sm_ticket[smid & 255u], 1u) & 3u;  // rotates the tie-break
+        unsigned int seen = *reinterpret_cast<volatile unsigned int *>(word), assumed;
+        uint32_t best;
+        do {
+            assumed = seen;
+            best = first;
+            for (uint32_t k = 1; k < 4; k++) {
+                const uint32_t sp = (first + k) & 3u;
+                if (((assumed >> (8 * sp)) & 0xffu) < ((assumed >> (8 * best)) & 0xffu)) best = sp;
+            }
+            seen = atomicCAS(word, assumed, assumed + (1u << (8 * best)));
+        } while (seen != assumed);
+        sm.rotation = best;
+        sm.subpart_mask = 0;
     }
     __syncthreads();
-    // rotate the roles over the warp slots so co-resident CTAs do not stack their entropy warps on one SMSP
-    const uint32_t role = (warp + sm.rotation) % 4u;
+    // roles by sub-partition: entropy on the chosen one, then predictor 0, predictor 1, emit on the following ones.
+    // %warpid is only a hint: if the four warps do not report four different sub-partitions, roles go by warp index.
+    uint32_t hw_warp;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
+    if (lane == 0) atomicOr(&sm.subpart_mask, 1u << (hw_warp & 3u));
+    __syncthreads();
+    const uint32_t role = ((sm.subpart_mask == 0xfu ? hw_warp : warp) - sm.rotation) & 3u;
+    if (g_role_cycles != nullptr && lane == 0) {  // developer aid: hardware warp slot of every warp of the CTA, by CTA warp index
+        uint32_t wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        reinterpret_cast<volatile uint8_t *>(g_role_cycles + (size_t)blockIdx.x * 16 + 14)[warp] = (uint8_t)wid;
+        if (warp == 0) {
+            reinterpret_cast<volatile uint8_t *>(g_role_cycles + (size_t)blockIdx.x * 16 + 14)[4] = (uint8_t)(sm.rotation & 3u);
+            g_role_cycles[(size_t)blockIdx.x * 16 + 15] = clock64();
+        }
+    }
     if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
     else if (role == 3) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
     else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
     __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicSub(&g_sm_entropy_load[smid & 255u], 1u << (8 * sm.rotation));
+    }
     // stage 3 reuses the window / ring / job memory as its transpose tile
     EmitArgs ea{packed, offsets, sizes, npackets, scratch, descs, pcm_out, out_stride};
     RoleTimer rt(lane, 8 + (int)(warp % 3u));

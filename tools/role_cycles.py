@@ -37,6 +37,11 @@ smid, wid = tag >> 8, tag & 255
 import collections
 per_sm = collections.defaultdict(list)
 for c in range(nct): per_sm[int(smid[c])].append((int(wid[c]), b[c,0]/1e6, (b[c,0]-b[c,1])/1e6))
+raw = buf.cpu().numpy().reshape(nct, 16)
+w14 = raw[:, 14].copy().view(np.uint8).reshape(nct, 8)
+print('hardware warp slots of CTA warps 0..3 (first 12 CTAs) + rotation:', [tuple(int(x) for x in w14[c, :5]) for c in range(12)])
+print('CTAs whose 4 warps sit on 4 distinct SMSPs:', int(sum(len(set(int(x) % 4 for x in w14[c, :4])) == 4 for c in range(nct))), 'of', nct)
+print('CTAs with warp w on SMSP w%4:', int(sum(all(int(w14[c, w]) % 4 == w for w in range(4)) for c in range(nct))))
 cnt = collections.Counter(len(v) for v in per_sm.values()); print('CTAs per SM histogram', dict(cnt))
 for k in (1,2,3,4):
     t=[x[1] for v in per_sm.values() if len(v)==k for x in v]
