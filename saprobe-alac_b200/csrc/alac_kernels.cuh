@@ -1714,6 +1714,100 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
     }
 }
 
+// ---- stage 3, row path: canonical multi-element packets (every element as long as the packet, the elements cover
+// every channel once, nothing spills). No transpose: each lane builds FR frames of ITS packet in a private shared-memory
+// row (element after element: batched parked-sample loads, un-mix, shift merge, byte placement at the element's
+// channel offset) and stores the row to its own packet slot with 128-bit stores. Frames past the packet's sample count
+// are written as zeros (decoder.go:120, :127). Four warps x 32 lanes x 16 parked-sample loads in flight per element
+// keep enough bytes in flight for the copy to be bandwidth- rather than latency-bound.
+template <int BPS, int FR, int NWARPS>
+__device__ __forceinline__ void emit_rows(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem, bool valid,
+                                          const Packet &pk, const PacketDesc *desc, uint32_t nops, uint32_t n_final,
+                                          uint32_t max_ops) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t fb = cfg.num_channels * BPS;            // bytes per frame
+    const uint32_t row_words = ((FR * fb) / 4u) | 1u;      // FR * fb is a multiple of 16; odd stride: conflict-free rows
+    constexpr uint32_t SHIFT_WORDS = (FR * 4 + 2 + 3 + 3) / 4 + 2;  // FR frames x 2 channels x 2 bytes + window + alignment
+    constexpr uint32_t SHIFT_ROW = SHIFT_WORDS | 1u;
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * 32u * (row_words + SHIFT_ROW);
+    uint32_t *roww = wbase + (size_t)lane * row_words;
+    uint8_t *row = reinterpret_cast<uint8_t *>(roww);
+    uint32_t *shrow = wbase + 32u * row_words + (size_t)lane * SHIFT_ROW;
+    const uint32_t pidx = group * 32u + lane;
+    const int32_t *sbase = x.scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+    uint8_t *slot = x.pcm_out + (size_t)pidx * x.out_stride;
+    const bool depth20 = cfg.bit_depth == 20;
+    const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;  // 16/20-bit writers ignore the shift buffer
+    const uint32_t nbatches = cfg.frame_length / FR;
+    const uint32_t nvec = (FR * fb) / 16u;
+#pragma unroll 1
+    for (uint32_t b = warp; b < nbatches; b += NWARPS) {
+        const uint32_t f0 = b * FR;
+#pragma unroll 1
+        for (uint32_t e = 0; e < max_ops; e++) {
+            if (e < nops) {
+                const OpDesc op = desc->ops[e];
+                const bool stereo = op.kind == 2;
+                const uint32_t width = stereo ? 2u : 1u;
+                const uint32_t sb = (merges_shift ? (uint32_t)op.shift : 0u) * 8u;
+                const int32_t i_lo = (int32_t)f0;
+                const int32_t i_hi = (int32_t)min(f0 + FR, op.n);
+                uint32_t rel0 = 0;
+                if (sb && i_hi > i_lo) {  // stage the shift bytes of these frames (zeros at or past the packet end, bitbuffer.go:36-51)
+                    const uint32_t first_bit = op.shift_bitpos + f0 * width * sb;
+                    const uint32_t nbits = (uint32_t)(i_hi - i_lo) * width * sb;
+                    const uint32_t byte0 = first_bit >> 3;
+                    const uint32_t nbytes = ((first_bit & 7u) + nbits + 7u) / 8u + 2u;  // +2: the 24-bit window of BitBuffer.Read
+                    const uintptr_t ga = ((uintptr_t)(pk.p + byte0)) & ~(uintptr_t)3;
+                    const uint32_t lead_bytes = (uint32_t)((uintptr_t)(pk.p + byte0) - ga);
+                    const int64_t rel_pk = (int64_t)byte0 - (int64_t)lead_bytes;
+                    const uint32_t nw = (lead_bytes + nbytes + 3u) / 4u;  // <= SHIFT_WORDS - 2
+                    const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(ga);
+#pragma unroll
+                    for (uint32_t k = 0; k < SHIFT_WORDS; k++) {
+                        const int64_t b_first = rel_pk + 4 * (int64_t)k;
+                        uint32_t w = 0;
+                        if (k < nw) {
+                            if (b_first + 4 <= (int64_t)pk.size) w = __ldg(gsrc + k);
+                            else
+                                for (int j = 0; j < 4; j++)
+                                    if (b_first + j >= 0 && b_first + j < (int64_t)pk.size) w |= (uint32_t)__ldg(pk.p + (b_first + j)) << (8 * j);
+                        }
+                        shrow[k] = w;
+                    }
+                    rel0 = lead_bytes * 8u + (first_bit & 7u);
+                }
+                EmitOp eo;
+                eo.su = sbase + (size_t)op.slot * cfg.frame_length * 32u;
+                eo.sv = stereo ? eo.su + (size_t)cfg.frame_length * 32u : eo.su;
+                eo.i_lo = i_lo; eo.i_hi = i_hi; eo.s0 = (int32_t)f0; eo.mix_res = op.mix_res; eo.mix_bits = op.mix_bits;
+                eo.sb = sb; eo.rel0 = rel0; eo.width = width; eo.fb = fb; eo.out_off = (uint32_t)op.out_chan * BPS;
+                eo.stereo = stereo; eo.depth20 = depth20;
+                emit_frames<BPS>(eo, row, shrow);
+            }
+        }
+        // the lane's own row -> its packet slot; bytes at or past n_final frames are zeros, and so is a packet
+        // without any element (END first, or failed)
+        const uint32_t n_rows = nops ? n_final : 0u;
+        const uint32_t nvalid = n_rows > f0 ? min((n_rows - f0) * fb, FR * fb) : 0u;
+        if (valid) {
+            uint4 *dst = reinterpret_cast<uint4 *>(slot + (size_t)f0 * fb);
+#pragma unroll 4
+            for (uint32_t k = 0; k < nvec; k++) {
+                uint32_t w[4];
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++) {
+                    const uint32_t byte = (4u * k + j) * 4u;
+                    uint32_t v = roww[4u * k + j];
+                    if (byte + 4u > nvalid) v = byte >= nvalid ? 0u : v & (0xffffffffu >> (8u * (byte + 4u - nvalid)));
+                    w[j] = v;
+                }
+                dst[k] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+}
+
 // Stage 3 runs warp-local: every warp owns a transpose tile of 32 packet rows x TL frames (+ a staging row for
 // the shift bytes) inside the shared memory the decode stage leaves behind, and walks the tiles w, w+NWARPS, ...
 // of the group on its own -- no block barrier, three tiles in flight per CTA.
@@ -1771,6 +1865,33 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
                 if (cfg.bps == 3) emit_direct<3, 1>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
                 else if (cfg.bps == 2) emit_direct<2, 1>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
                 else emit_direct<4, 1>(x, cfg, group, smem, valid, pk, op0, n_final, first_frame);
+            }
+            return;
+        }
+    }
+    // row path when every packet of the group is canonical: all elements as long as the packet, every channel covered
+    // once, no pair spilling past the last channel; and the shapes allow whole 128-bit row stores
+    {
+        bool canon = true;
+        uint32_t chans = 0;  // channels written so far
+        for (uint32_t e = 0; e < nops; e++) {
+            const OpDesc op = desc->ops[e];
+            const uint32_t w = op.kind == 2 ? 2u : 1u;
+            const uint32_t m = ((1u << w) - 1u) << op.out_chan;
+            canon = canon && op.n == n_final && (uint32_t)op.out_chan + w <= cfg.num_channels && (chans & m) == 0u;
+            chans |= m;
+        }
+        canon = !valid || nops == 0 || (canon && chans == (1u << cfg.num_channels) - 1u);
+        const uint32_t FR = (fb & 1u) ? 16u : 8u;  // frames per row: FR * fb must be a multiple of 16
+        const uint32_t need = NWARPS * 32u * 4u * ((((FR * fb) / 4u) | 1u) + ((((FR * 4u + 8u) / 4u) + 2u) | 1u));
+        const bool vec_ok = ((((uintptr_t)x.pcm_out) | x.out_stride) & 15u) == 0;
+        if (__all_sync(FULL_MASK, canon) && vec_ok && cfg.frame_length % FR == 0 && need <= smem_bytes) {
+            if (FR == 8u) {
+                if (cfg.bps == 3) emit_rows<3, 8, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, n_final, max_ops);
+                else if (cfg.bps == 2) emit_rows<2, 8, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, n_final, max_ops);
+                else emit_rows<4, 8, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, n_final, max_ops);
+            } else {
+                emit_rows<3, 16, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, n_final, max_ops);  // odd frame size: 24-bit only
             }
             return;
         }
