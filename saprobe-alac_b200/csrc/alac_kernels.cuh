@@ -1720,6 +1720,10 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
 // channel offset) and stores the row to its own packet slot with 128-bit stores. Frames past the packet's sample count
 // are written as zeros (decoder.go:120, :127). Four warps x 32 lanes x 16 parked-sample loads in flight per element
 // keep enough bytes in flight for the copy to be bandwidth- rather than latency-bound.
+// 32-bit words of shift data staged per lane and element: FR frames x 2 channels x 2 bytes + the 24-bit window of
+// BitBuffer.Read, fetched as whole 16-byte pieces
+__host__ __device__ constexpr uint32_t row_shift_words(uint32_t fr) { return ((fr * 4u + 2u + 15u + 15u) / 16u) * 4u; }
+
 template <int BPS, int FR, int NWARPS>
 __device__ __forceinline__ void emit_rows(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem, bool valid,
                                           const Packet &pk, const PacketDesc *desc, uint32_t nops, uint32_t n_final,
@@ -1727,7 +1731,7 @@ __device__ __forceinline__ void emit_rows(const EmitArgs &x, const DevConfig &cf
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t fb = cfg.num_channels * BPS;            // bytes per frame
     const uint32_t row_words = ((FR * fb) / 4u) | 1u;      // FR * fb is a multiple of 16; odd stride: conflict-free rows
-    constexpr uint32_t SHIFT_WORDS = (FR * 4 + 2 + 3 + 3) / 4 + 2;  // FR frames x 2 channels x 2 bytes + window + alignment
+    constexpr uint32_t SHIFT_WORDS = row_shift_words(FR);
     constexpr uint32_t SHIFT_ROW = SHIFT_WORDS | 1u;
     uint32_t *wbase = reinterpret_cast<uint32_t *>(smem) + (size_t)warp * 32u * (row_words + SHIFT_ROW);
     uint32_t *roww = wbase + (size_t)lane * row_words;
@@ -1750,40 +1754,79 @@ __device__ __forceinline__ void emit_rows(const EmitArgs &x, const DevConfig &cf
                 const bool stereo = op.kind == 2;
                 const uint32_t width = stereo ? 2u : 1u;
                 const uint32_t sb = (merges_shift ? (uint32_t)op.shift : 0u) * 8u;
-                const int32_t i_lo = (int32_t)f0;
-                const int32_t i_hi = (int32_t)min(f0 + FR, op.n);
+                const uint32_t cnt = op.n > f0 ? min((uint32_t)FR, op.n - f0) : 0u;
+                // ---- every load of this element's FR frames is issued before anything waits: parked samples ...
+                const int32_t *su = sbase + (size_t)op.slot * cfg.frame_length * 32u;
+                const int32_t *sv = stereo ? su + (size_t)cfg.frame_length * 32u : su;
+                const uint32_t last = op.n > 0 ? op.n - 1u : 0u;
+                int32_t lu[FR], lv[FR];
+#pragma unroll
+                for (int q = 0; q < FR; q++) {
+                    const uint32_t i = min(f0 + (uint32_t)q, last);
+                    lu[q] = __ldcs(su + (size_t)i * 32u);  // parked samples are read exactly once
+                    lv[q] = __ldcs(sv + (size_t)i * 32u);
+                }
+                // ... and the shift bytes of these frames (zeros at or past the packet end, bitbuffer.go:36-51)
                 uint32_t rel0 = 0;
-                if (sb && i_hi > i_lo) {  // stage the shift bytes of these frames (zeros at or past the packet end, bitbuffer.go:36-51)
+                if (sb && cnt) {
                     const uint32_t first_bit = op.shift_bitpos + f0 * width * sb;
-                    const uint32_t nbits = (uint32_t)(i_hi - i_lo) * width * sb;
+                    const uint32_t nbits = cnt * width * sb;
                     const uint32_t byte0 = first_bit >> 3;
                     const uint32_t nbytes = ((first_bit & 7u) + nbits + 7u) / 8u + 2u;  // +2: the 24-bit window of BitBuffer.Read
-                    const uintptr_t ga = ((uintptr_t)(pk.p + byte0)) & ~(uintptr_t)3;
+                    const uintptr_t ga = ((uintptr_t)(pk.p + byte0)) & ~(uintptr_t)15;  // 16-byte pieces: few requests per lane
                     const uint32_t lead_bytes = (uint32_t)((uintptr_t)(pk.p + byte0) - ga);
                     const int64_t rel_pk = (int64_t)byte0 - (int64_t)lead_bytes;
                     const uint32_t nw = (lead_bytes + nbytes + 3u) / 4u;  // <= SHIFT_WORDS - 2
-                    const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(ga);
+                    uint32_t wbuf[SHIFT_WORDS];
+                    if (rel_pk >= 0 && rel_pk + 4 * (int64_t)SHIFT_WORDS <= (int64_t)pk.size) {  // the whole window lies inside the packet
+                        const uint4 *g4 = reinterpret_cast<const uint4 *>(ga);
 #pragma unroll
-                    for (uint32_t k = 0; k < SHIFT_WORDS; k++) {
-                        const int64_t b_first = rel_pk + 4 * (int64_t)k;
-                        uint32_t w = 0;
-                        if (k < nw) {
-                            if (b_first + 4 <= (int64_t)pk.size) w = __ldg(gsrc + k);
-                            else
+                        for (uint32_t k = 0; k < SHIFT_WORDS / 4; k++) {
+                            const uint4 v = __ldg(g4 + k);
+                            wbuf[4 * k] = v.x; wbuf[4 * k + 1] = v.y; wbuf[4 * k + 2] = v.z; wbuf[4 * k + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (uint32_t k = 0; k < SHIFT_WORDS; k++) {
+                            const int64_t b_first = rel_pk + 4 * (int64_t)k;
+                            uint32_t w = 0;
+                            if (k < nw)
                                 for (int j = 0; j < 4; j++)
                                     if (b_first + j >= 0 && b_first + j < (int64_t)pk.size) w |= (uint32_t)__ldg(pk.p + (b_first + j)) << (8 * j);
+                            shrow[k] = w;
                         }
-                        shrow[k] = w;
+#pragma unroll
+                        for (uint32_t k = 0; k < SHIFT_WORDS; k++) wbuf[k] = shrow[k];
                     }
+#pragma unroll
+                    for (uint32_t k = 0; k < SHIFT_WORDS; k++) shrow[k] = wbuf[k];
                     rel0 = lead_bytes * 8u + (first_bit & 7u);
                 }
-                EmitOp eo;
-                eo.su = sbase + (size_t)op.slot * cfg.frame_length * 32u;
-                eo.sv = stereo ? eo.su + (size_t)cfg.frame_length * 32u : eo.su;
-                eo.i_lo = i_lo; eo.i_hi = i_hi; eo.s0 = (int32_t)f0; eo.mix_res = op.mix_res; eo.mix_bits = op.mix_bits;
-                eo.sb = sb; eo.rel0 = rel0; eo.width = width; eo.fb = fb; eo.out_off = (uint32_t)op.out_chan * BPS;
-                eo.stereo = stereo; eo.depth20 = depth20;
-                emit_frames<BPS>(eo, row, shrow);
+                // ---- un-mix, merge, place the bytes at the element's channel offset of every frame ----
+                const int32_t mix_res = op.mix_res;
+                const uint32_t mix_bits = op.mix_bits;
+                uint8_t *dstb = row + (uint32_t)op.out_chan * BPS;
+#pragma unroll
+                for (int q = 0; q < FR; q++) {
+                    if ((uint32_t)q < cnt) {
+                        int32_t left = lu[q], right = stereo ? lv[q] : 0;
+                        if (stereo && mix_res != 0) {  // matrix.go:40-41
+                            const int32_t v = right;
+                            left = left + v - sar_go(mix_res * v, mix_bits);
+                            right = left - v;
+                        }
+                        if (depth20) {
+                            left = (int32_t)((uint32_t)left << 4);
+                            right = (int32_t)((uint32_t)right << 4);
+                        }
+                        if (sb) {  // shift buffer merge, matrix.go:132-135, :270-272 (BitBuffer.Read of sb bits)
+                            const uint32_t rel = rel0 + (uint32_t)q * width * sb;
+                            left = (int32_t)shl_go((uint32_t)left, sb) | (int32_t)shift_field(shrow, rel, sb);
+                            if (stereo) right = (int32_t)shl_go((uint32_t)right, sb) | (int32_t)shift_field(shrow, rel + sb, sb);
+                        }
+                        tile_store<BPS>(dstb + (uint32_t)q * fb, left, right, stereo);
+                    }
+                }
             }
         }
         // the lane's own row -> its packet slot; bytes at or past n_final frames are zeros, and so is a packet
@@ -1883,7 +1926,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
         }
         canon = !valid || nops == 0 || (canon && chans == (1u << cfg.num_channels) - 1u);
         const uint32_t FR = (fb & 1u) ? 16u : 8u;  // frames per row: FR * fb must be a multiple of 16
-        const uint32_t need = NWARPS * 32u * 4u * ((((FR * fb) / 4u) | 1u) + ((((FR * 4u + 8u) / 4u) + 2u) | 1u));
+        const uint32_t need = NWARPS * 32u * 4u * ((((FR * fb) / 4u) | 1u) + (row_shift_words(FR) | 1u));
         const bool vec_ok = ((((uintptr_t)x.pcm_out) | x.out_stride) & 15u) == 0;
         if (__all_sync(FULL_MASK, canon) && vec_ok && cfg.frame_length % FR == 0 && need <= smem_bytes) {
             if (FR == 8u) {
