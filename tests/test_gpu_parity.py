@@ -254,6 +254,49 @@ def test_mixed_group_live_and_fallback(pkg):
     assert (st != 0).any() and (st == 0).sum() > 200
 
 
+def test_mixed_groups_multichannel_tail(pkg):
+    """Multi-channel batches whose 32-packet groups mix canonical packets (row-path tail) with packets that force the
+    transpose-tile tail (under-filled, pairs first / spilling, mixed per-element counts, END-only, broken): whole groups
+    of one kind, and groups where a single odd packet sits among canonical ones."""
+    for ch, bits in ((6, 16), (8, 24), (3, 24), (5, 20)):
+        ocfg = ol.Config.make(bit_depth=bits, num_channels=ch, sample_rate=48000)
+        x = make_signal('silence_lsb', ch, 4096 * 6, bits, 48000, seed=40 + ch)
+        canon = ol.encode_stream(ocfg, x)
+        shifted = ol.encode_stream(ocfg, x, ol.PacketOpts.make(bytes_shifted=1)) if bits >= 24 else canon
+        a = x[:4096, 0].copy()
+        b = (x[:4096, 1] // 2).copy()
+        under = ol.Writer(ocfg).element(0, a, order=4, coefs=[60, -30, 10, 5]).end().bytes()
+        w = ol.Writer(ocfg)
+        idx = 0
+        while idx + 2 <= ch:
+            w.element(1, a, b, order=4, coefs=[80, -40, 20, -10])
+            idx += 2
+        if idx < ch:
+            w.element(0, b, order=6, coefs=[90, -45, 22, -11, 5, -2])
+        pairs_first = w.end().bytes()
+        w = ol.Writer(ocfg)
+        for k in range(ch):
+            nk = [4096, 100, 4096, 7, 2000, 1, 4096, 333][k]
+            w.element(0, a[:nk], order=[4, 0, 31, 2, 5, 6, 8, 9][k], coefs=[40, -20, 10, -5, 2, -1, 1, 0, 0], partial=1)
+        mixed_counts = w.end().bytes()
+        end_only = ol.Writer(ocfg).end().bytes()
+        partial = ol.encode_packet(ocfg, x[:1500])
+        broken = bytes(bytearray(canon[0])[:len(canon[0]) // 2])
+        odd = [under, pairs_first, mixed_counts, end_only, partial, broken]
+        packets = []
+        for i in range(32 * 6 + 11):
+            g, l = divmod(i, 32)
+            if g == 0: p = canon[i % 6]                      # all canonical
+            elif g == 1: p = shifted[i % 6]                  # all canonical, shift buffer
+            elif g == 2: p = odd[l % 6]                      # none canonical
+            elif g == 3: p = odd[(l // 5) % 6] if l % 5 == 0 else canon[i % 6]
+            elif g == 4: p = end_only if l == 9 else partial  # same short count + an empty packet: still canonical
+            else: p = canon[i % 6] if l != 21 else odd[g % 6]
+            packets.append(p)
+        _, _, st = assert_parity(pkg, ocfg, packets, f'multichannel mixed c{ch} d{bits}')
+        assert (st == 0).sum() > 150
+
+
 def test_full_size_c3_shift_buffer_stream(pkg):
     """BASELINE configs[2] at full size: 1 h of 24-bit stereo 192 kHz, 168 750 packets, every element header carries
     bytesShifted=1. Size-independent checks: every packet OK, byte count, and the digest of the whole PCM stream equals
