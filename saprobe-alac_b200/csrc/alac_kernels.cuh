@@ -202,7 +202,7 @@ struct DecShared {
     uint64_t full_bar[2][RING_SLOTS];
     uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
     uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
-    volatile uint32_t u_streams_done;   // streams the U/mono predictor warp has finished (release/acquire by fences)
+    volatile uint32_t u_chunks_done;    // ring slots the U/mono predictor warp has finished and parked (release/acquire by fences)
     uint32_t rotation;                  // sub-partition chosen for the entropy warp of this CTA
     uint32_t subpart_mask;              // sub-partitions the four warps report
 };
@@ -467,7 +467,7 @@ struct StreamSpec {
     uint32_t coef_bitpos;  // where the consumer finds the 16-bit coefficients
     uint32_t live;         // V of a pair in a 2-channel stream: bit 31 set, mixBits | mixRes<<8 | bytesShifted<<16
     uint32_t shift_bitpos;
-    uint32_t u_streams;    // number of U/mono streams that must be finished before the last parked samples are read
+    uint32_t u_streams;    // consumer-0 sequence number of the first ring slot of this pair's U stream
 };
 
 // ---- 16 samples without a branch ------------------------------------------------------------------------------
@@ -793,7 +793,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     bool parsing = valid;
     if (valid && pk.size > 0x0FFFFFFFu) { st = ST_REF_PANIC; parsing = false; }  // bit positions are 32-bit here
     uint32_t seq[2] = {0, 0};
-    uint32_t nstreams0 = 0;  // streams handed to the U/mono predictor warp so far
+    uint32_t u_first = 0;    // consumer-0 sequence number at which the current element's U / mono stream starts
     bool quiet = false;      // warp-uniform: run-length codes keep appearing, decode them in line (decode_batch<true>)
     BitReader br;
     br.fifo = fifo_addr;
@@ -861,11 +861,11 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                     st = ST_REF_PANIC | ctx;
             }
             const int32_t before = st;
-            if (pass != 1) nstreams0++;
+            if (pass != 1) u_first = seq[0];
             if (pass == 1 && live_round) {
                 a.live = 0x80000000u | (h.mix_bits & 0xffu) | (((uint32_t)h.mix_res & 0xffu) << 8) | (h.shift << 16);
                 a.shift_bitpos = h.shift_bitpos;
-                a.u_streams = nstreams0;
+                a.u_streams = u_first;
             }
             produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, quiet, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
@@ -1187,6 +1187,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
     RoleTimer rt(lane, 12);
     const unsigned long long t_start = rt.now();
     uint32_t seq = 0;
+    uint32_t u_seen = 0;  // consumer-0 ring slots known to be parked (acquired)
 #pragma unroll 1
     for (;;) {
         // first slot of a stream: its job
@@ -1212,10 +1213,13 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
             par = (seq / RING_SLOTS) & 1u;
             uint32_t rel0 = 0;
             if (live_any) {
-                if (ck + 4u >= nchunks) {
-                    // the last parked U samples: the U predictor warp must have finished its stream
-                    while (sm.u_streams_done < u_streams) __nanosleep(64);
-                    __threadfence_block();
+                // the U predictor warp must have parked chunk ck of this pair's U stream (it normally did long ago)
+                if (u_seen < u_streams + ck + 1u) {  // warp-uniform; one acquire covers everything published before it
+                    if (lane == 0) {
+                        while ((u_seen = sm.u_chunks_done) < u_streams + ck + 1u) __nanosleep(64);
+                        __threadfence_block();
+                    }
+                    u_seen = __shfl_sync(FULL_MASK, u_seen, 0);
                 }
                 live_prefetch(sm, lane, lc, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
             }
@@ -1240,6 +1244,16 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
     }
     rt.add(0, t_start);
     rt.flush(2);
+}
+
+// The U / mono predictor warp has parked everything up to ring slot `seq` of its consumer: release it to the emit warp,
+// which reads the parked samples back through L2 (cp.async.cg).
+__device__ __forceinline__ void publish_parked(DecShared &sm, uint32_t lane, uint32_t seq) {
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();  // writer and reader share the CTA (and the SM's path to L2, which the reader's cp.async.cg takes)
+        sm.u_chunks_done = seq;
+    }
 }
 
 // Register predictor: orders 4/5/6/8 with int32 coefficients (unpcBlock4/5/6/8, predictor.go:99-618), plus
@@ -1339,6 +1353,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
         if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
+        if (cons == 0 && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
 }
 
@@ -1407,6 +1422,7 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
         if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
+        if (cons == 0 && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
 }
 
@@ -1430,7 +1446,6 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
     lc.bit_depth = cfg.bit_depth;
     lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
     lc.enabled = cons == 1 && cfg.num_channels == 2u;
-    uint32_t streams_done = 0;
     RoleTimer rt(lane, 3 + 2 * cons);
     const unsigned long long t_start = rt.now();
 #pragma unroll 1
@@ -1477,14 +1492,6 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
             else stream_reg<6, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
         } else if (any8) stream_reg<8, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
         else stream_reg<6, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        if (cons == 0) {  // publish "this U/mono stream is parked" for the V warp's live emission
-            streams_done++;
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                sm.u_streams_done = streams_done;
-            }
-        }
     }
     rt.add(0, t_start);
     rt.flush(3);
@@ -2084,7 +2091,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
                 mbar_init(&sm.empty_bar[c][s], c == 1 ? 64 : 32);
             }
         for (int s = 0; s < RING_SLOTS; s++) mbar_init(&sm.vdone_bar[s], 32);
-        sm.u_streams_done = 0;
+        sm.u_chunks_done = 0;
         // The hardware puts the four warps of a CTA on the four SM sub-partitions (one each, starting anywhere), and the
         // entropy warp is the one that must not share a scheduler with another entropy warp. Per SM, a packed word
         // counts the resident entropy warps of every sub-partition; the CTA puts its own on the least loaded one.
