@@ -194,7 +194,7 @@ struct DecShared {
     uint4 fifo[32][FIFO_CHUNKS];
     int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (16 KB)
     uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
-                                             // live-emit word, shift bit position, U streams to wait for
+                                             // live-emit word, shift bit position, first consumer-0 slot of the U stream
     // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
     int32_t live_u[CHUNK][32];
     uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
@@ -467,7 +467,7 @@ struct StreamSpec {
     uint32_t coef_bitpos;  // where the consumer finds the 16-bit coefficients
     uint32_t live;         // V of a pair in a 2-channel stream: bit 31 set, mixBits | mixRes<<8 | bytesShifted<<16
     uint32_t shift_bitpos;
-    uint32_t u_streams;    // consumer-0 sequence number of the first ring slot of this pair's U stream
+    uint32_t u_first_slot;    // consumer-0 sequence number of the first ring slot of this pair's U stream
 };
 
 // ---- 16 samples without a branch ------------------------------------------------------------------------------
@@ -573,7 +573,7 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
             sm.job[cons][slot][3][lane] = nmax;
             sm.job[cons][slot][4][lane] = active ? sp.live : 0u;
             sm.job[cons][slot][5][lane] = sp.shift_bitpos;
-            sm.job[cons][slot][6][lane] = sp.u_streams;
+            sm.job[cons][slot][6][lane] = sp.u_first_slot;
             if (pair) {
                 sm.job[1][slot2][0][lane] = sp2.n;
                 sm.job[1][slot2][1][lane] = active ? sp2.meta : (uint32_t)JOB_INACTIVE;
@@ -810,7 +810,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         StreamSpec s0, s1;
         s0.live = s1.live = 0;
         s0.shift_bitpos = s1.shift_bitpos = 0;
-        s0.u_streams = s1.u_streams = 0;
+        s0.u_first_slot = s1.u_first_slot = 0;
         // 2-channel streams whose 32 packets all carry one compressed pair: the V predictor warp emits PCM itself
         const bool live_round = cfg.num_channels == 2u && !(g_debug_flags & 1u) &&
                                 __all_sync(FULL_MASK, !valid || (h.have && h.stereo && !h.escape && st == ST_OK &&
@@ -865,7 +865,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
             if (pass == 1 && live_round) {
                 a.live = 0x80000000u | (h.mix_bits & 0xffu) | (((uint32_t)h.mix_res & 0xffu) << 8) | (h.shift << 16);
                 a.shift_bitpos = h.shift_bitpos;
-                a.u_streams = u_first;
+                a.u_first_slot = u_first;
             }
             produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, quiet, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
@@ -944,7 +944,7 @@ __device__ __forceinline__ int32_t delta_step(bool on, int32_t &prev, int32_t r,
 }
 
 struct Job {
-    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax, live, shift_bitpos, u_streams;
+    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax, live, shift_bitpos, u_first_slot;
 };
 
 // sb (8 or 16) bits at bit offset `rel` of a staged shift row (bytes in stream order, 32-bit words as loaded)
@@ -1201,7 +1201,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
         const uint32_t nmax = __shfl_sync(FULL_MASK, sm.job[1][slot][3][lane], 0);
         const uint32_t live_word = sm.job[1][slot][4][lane];
         const uint32_t shift_bitpos = sm.job[1][slot][5][lane];
-        const uint32_t u_streams = __shfl_sync(FULL_MASK, sm.job[1][slot][6][lane], 0);
+        const uint32_t u_first_slot = __shfl_sync(FULL_MASK, sm.job[1][slot][6][lane], 0);
         const bool live_lane = valid && (meta & 3u) != JOB_INACTIVE && (live_word >> 31) != 0u;
         const bool live_any = __any_sync(FULL_MASK, live_lane);
         const uint32_t n_lane = live_lane ? n : 0u;
@@ -1214,9 +1214,9 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
             uint32_t rel0 = 0;
             if (live_any) {
                 // the U predictor warp must have parked chunk ck of this pair's U stream (it normally did long ago)
-                if (u_seen < u_streams + ck + 1u) {  // warp-uniform; one acquire covers everything published before it
+                if (u_seen < u_first_slot + ck + 1u) {  // warp-uniform; one acquire covers everything published before it
                     if (lane == 0) {
-                        while ((u_seen = sm.u_chunks_done) < u_streams + ck + 1u) __nanosleep(64);
+                        while ((u_seen = sm.u_chunks_done) < u_first_slot + ck + 1u) __nanosleep(64);
                         __threadfence_block();
                     }
                     u_seen = __shfl_sync(FULL_MASK, u_seen, 0);
@@ -1461,7 +1461,7 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
         jb.nmax = sm.job[cons][slot][3][lane];
         jb.live = sm.job[cons][slot][4][lane];
         jb.shift_bitpos = sm.job[cons][slot][5][lane];
-        jb.u_streams = sm.job[cons][slot][6][lane];
+        jb.u_first_slot = sm.job[cons][slot][6][lane];
         jb.kind = meta & 3u;
         if (jb.kind == JOB_EXIT) {  // written for every lane
             if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);  // pass it on to the emit warp
