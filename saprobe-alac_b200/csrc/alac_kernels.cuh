@@ -483,7 +483,7 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
                                              uint32_t a0, uint32_t a_last) {
     bool saw_run = false;
     const uint32_t a_end = a0 + (CHUNK / 2) * 128u;
-#pragma unroll 2
+#pragma unroll (QUIET ? 2 : 4)
     for (uint32_t aj = a0; aj != a_end; aj += 128u) {
         const uint32_t n0 = br.load(br.qo);  // the word after lo
         const uint32_t w = br.window();
@@ -963,6 +963,7 @@ struct LiveCtx {
     PacketDesc *desc;
     uint32_t frame_length, bps, bit_depth;
     bool vec_ok, enabled;
+    bool publish;  // U / mono predictor warp of a 2-channel stream: the emit warp reads its parked samples back
 };
 
 // Start fetching what the emission of chunk `ck` needs: the parked U samples of the 32 frames (one 4 KB block,
@@ -1264,6 +1265,7 @@ template <int T, bool MODE, bool LIVE>
 __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
                                            const LiveCtx &lc) {
+    const bool lc_publish = lc.publish;
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
@@ -1353,14 +1355,15 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
         if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
-        if (cons == 0 && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
+        if (lc_publish && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
 }
 
 // Any mix of orders in the warp, including the int16-wrapping ones: unpcBlockGeneral, predictor.go:623-684,
 // with per-lane coefficient width (int32 kept for 4/5/6/8 as the reference's specialised loops do).
 __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
-                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt) {
+                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
+                                            bool lc_publish) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
@@ -1422,7 +1425,7 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
         if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
         seq++;
-        if (cons == 0 && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
+        if (lc_publish && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
 }
 
@@ -1446,6 +1449,7 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
     lc.bit_depth = cfg.bit_depth;
     lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
     lc.enabled = cons == 1 && cfg.num_channels == 2u;
+    lc.publish = cons == 0 && cfg.num_channels == 2u;
     RoleTimer rt(lane, 3 + 2 * cons);
     const unsigned long long t_start = rt.now();
 #pragma unroll 1
@@ -1480,7 +1484,7 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int
         const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
         // live emission (2-channel streams, V warp): decided per stream by the entropy warp, uniform over the warp
         const bool live = lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
-        if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt);
+        if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt, lc.publish);
         else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
             if (live) {
                 if (any8) stream_reg<8, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
