@@ -1,8 +1,8 @@
 // alac_abi.cu -- the C ABI of include/alac_b200.h over the kernels in alac_kernels.cuh.
 //
-// Host-side plumbing only: handles, device buffers, the chunked H2D -> decode -> emit -> D2H pipeline
-// on three CUDA streams, pinned memory, error text. No decode arithmetic lives here and there is no
-// CPU fallback: if CUDA is unusable every decode entry point fails.
+// Host-side plumbing only: handles, device buffers, the chunked H2D -> decode kernel -> D2H pipeline over
+// four slots (a CUDA stream and its buffers each), pinned memory, error text. No decode arithmetic lives
+// here and there is no CPU fallback: if CUDA is unusable every decode entry point fails.
 #include "alac_kernels.cuh"
 
 #include <algorithm>
@@ -80,7 +80,7 @@ struct PinBuf {
     }
 };
 
-// Scratch shared by decode + emit for one in-flight batch.
+// What one in-flight batch needs besides its inputs and outputs: the parked samples and the element lists.
 struct Work {
     DevBuf scratch;  // int32 [groups][channels][frame_length][32]
     DevBuf descs;    // PacketDesc [n]
@@ -140,7 +140,7 @@ int32_t check_config(const alacb200_config *cfg) {
 }
 
 
-// Enqueue decode + emit for n device-resident packets on `stream`.
+// Enqueue the decode kernel for n device-resident packets on `stream`.
 int32_t launch(alacb200_decoder *dec, Work &work, const uint8_t *d_packed, const uint64_t *d_offsets,
                const uint32_t *d_sizes, uint32_t n, uint8_t *d_pcm, uint64_t out_stride, uint32_t *d_out_bytes,
                int32_t *d_status, cudaStream_t stream) {
@@ -379,6 +379,21 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
     while (chunk > 32u && (uint64_t)chunk * out_stride > max_chunk_pcm) chunk /= 2u;
     chunk = (chunk + 31u) & ~31u;
 
+    // Whatever way this call ends, nothing may still be copying into the caller's buffers afterwards and no slot may
+    // keep pointers into the caller's arrays for a later call to write through.
+    struct Drain {
+        alacb200_decoder *d;
+        bool clean = false;  // every slot was retired: nothing in flight
+        ~Drain() {
+            for (auto &s : d->slots) {
+                if (!clean) cudaStreamSynchronize(s.stream);
+                s.pending = 0;
+                s.user_out_bytes = nullptr;
+                s.user_status = nullptr;
+            }
+        }
+    } drain{dec};
+
     int32_t rc = ALACB200_OK;
     uint32_t slot_idx = 0;
     auto retire = [](Slot &s) -> bool {  // wait for the slot's chunk and hand its per-packet results to the caller
@@ -434,6 +449,7 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
     }
     for (auto &s : dec->slots)
         if (!retire(s)) return ALACB200_E_CUDA;
+    drain.clean = rc == ALACB200_OK;
     return rc;
 }
 
