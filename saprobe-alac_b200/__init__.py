@@ -233,7 +233,11 @@ class PacketDecoder:
             lib.alacb200_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the module globals may already be gone
+            pass
 
     def Format(self) -> PCMFormat:
         f = _PcmFormatC()
