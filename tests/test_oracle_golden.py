@@ -67,3 +67,31 @@ def test_encoder_roundtrip_all_depths():
             if bits == 20:
                 y = y >> 4
             assert np.array_equal(y, x), (bits, shift, ch)
+
+
+def test_synthetic_cases_are_well_formed_for_the_oracle():
+    """The synthetic suites the GPU parity tests use: exotic cases decode (or hit a reference panic), hostile packets end in one of the
+    reference's sentinels (or where it would panic), and the threaded batch driver equals packet-by-packet decoding."""
+    import synth_cases
+    n_exotic = n_hostile = 0
+    for name, cfg, packets in synth_cases.exotic_cases():
+        for p in packets:
+            st, pcm = ol.decode_packet(cfg, p)
+            assert (pcm is None) == (st != ol.OK), name
+            # the only exotic shapes that do not decode are the ones on which the reference panics (appendix B7)
+            assert st == ol.OK or ol.code(st) == 9, (name, st)
+            n_exotic += st == ol.OK
+    seen = set()
+    for name, cfg, packets in synth_cases.hostile_cases(max_per_seed=12):
+        packed, offs, sizes = ol.pack(packets)
+        out, nb, status = ol.decode_batch(cfg, packed, offs, sizes, nthreads=3)
+        for i, p in enumerate(packets):
+            n_hostile += 1
+            st, pcm = ol.decode_packet(cfg, p)
+            assert st == status[i], name
+            assert (pcm is None) == (st != ol.OK), name
+            if pcm is not None:
+                assert bytes(out[i, :nb[i]]) == pcm, name
+            seen.add(ol.code(st))
+    assert n_exotic > 200 and n_hostile > 300
+    assert seen <= {0, 3, 4, 5, 6, 7, 9}, seen
