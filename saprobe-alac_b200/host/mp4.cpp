@@ -6,6 +6,7 @@
 // never read, the first trak with an 'alac' sample entry wins, a trak whose stsd is unusable is skipped.
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -17,12 +18,13 @@ struct Reader {  // io.ReadSeeker over a byte image
     const uint8_t *data;
     int64_t len;
     int64_t pos;
+    bool has(int64_t n) const { return pos >= 0 && pos <= len && n >= 0 && n <= len - pos; }
     bool read_full(uint8_t *dst, int64_t n) {  // io.ReadFull
         if (pos < 0 || pos > len || n > len - pos) {
             pos = len;
             return false;
         }
-        std::memcpy(dst, data + pos, (size_t)n);
+        if (n > 0) std::memcpy(dst, data + pos, (size_t)n);  // dst may be null for an empty table
         pos += n;
         return true;
     }
@@ -148,6 +150,7 @@ bool build_sample_table(Reader &r, const Box &stbl, std::vector<alacb200_sample_
     if (find_child(r, stbl, "stco", box, found, e2) && found) {
         if (!read_table(r, box, 8, hdr)) { err = "mp4: no chunk offset box (stco/co64)"; return false; }
         uint32_t count = be32(&hdr[4]);
+        if (!r.has((int64_t)count * 4)) { err = "mp4: no chunk offset box (stco/co64)"; return false; }  // before any allocation
         buf.resize((size_t)count * 4);
         if (!r.read_full(buf.data(), (int64_t)count * 4)) { err = "mp4: no chunk offset box (stco/co64)"; return false; }
         chunk_offsets.resize(count);
@@ -156,6 +159,7 @@ bool build_sample_table(Reader &r, const Box &stbl, std::vector<alacb200_sample_
         if (!find_child(r, stbl, "co64", box, found, e2) || !found) { err = "mp4: no chunk offset box (stco/co64)"; return false; }
         if (!read_table(r, box, 8, hdr)) { err = "mp4: invalid co64 payload"; return false; }
         uint32_t count = be32(&hdr[4]);
+        if (!r.has((int64_t)count * 8)) { err = "mp4: invalid co64 payload"; return false; }
         buf.resize((size_t)count * 8);
         if (!r.read_full(buf.data(), (int64_t)count * 8)) { err = "mp4: invalid co64 payload"; return false; }
         chunk_offsets.resize(count);
@@ -165,6 +169,7 @@ bool build_sample_table(Reader &r, const Box &stbl, std::vector<alacb200_sample_
     if (!find_child(r, stbl, "stsc", box, found, e2) || !found) { err = "mp4: no stsc box"; return false; }
     if (!read_table(r, box, 8, hdr)) { err = "mp4: invalid stsc payload"; return false; }
     uint32_t nstsc = be32(&hdr[4]);
+    if (!r.has((int64_t)nstsc * 12)) { err = "mp4: invalid stsc payload"; return false; }
     buf.resize((size_t)nstsc * 12);
     if (!r.read_full(buf.data(), (int64_t)nstsc * 12)) { err = "mp4: invalid stsc payload"; return false; }
     std::vector<std::pair<uint32_t, uint32_t>> stsc(nstsc);
@@ -175,21 +180,24 @@ bool build_sample_table(Reader &r, const Box &stbl, std::vector<alacb200_sample_
     uint32_t constant = be32(&hdr[4]), count = be32(&hdr[8]);
     std::vector<uint32_t> sizes;
     if (constant == 0) {
+        if (!r.has((int64_t)count * 4)) { err = "mp4: invalid stsz payload"; return false; }
         buf.resize((size_t)count * 4);
         if (!r.read_full(buf.data(), (int64_t)count * 4)) { err = "mp4: invalid stsz payload"; return false; }
         sizes.resize(count);
         for (uint32_t i = 0; i < count; i++) sizes[i] = be32(&buf[(size_t)i * 4]);
     }
     out.clear();
+    // A table cannot name more samples than the image has bytes (a constant-size stsz carries no per-sample data, so its
+    // count is otherwise unbounded; the reference would try to allocate it).
+    if ((int64_t)count > r.len) { err = "mp4: invalid stsz payload"; return false; }
     out.reserve(count);
     uint64_t sample_idx = 0;
-    for (size_t ci = 0; ci < chunk_offsets.size(); ci++) {
-        // lookupSamplesPerChunk, mp4.go:580-591 (1-based chunk numbers)
-        uint32_t per = 0;
-        for (auto &en : stsc) {
-            if (en.first > (uint32_t)(ci + 1)) break;
-            per = en.second;
-        }
+    size_t k = 0;  // first stsc entry whose first_chunk exceeds the current chunk number: it only ever moves forward
+    for (size_t ci = 0; ci < chunk_offsets.size() && sample_idx < count; ci++) {
+        // lookupSamplesPerChunk, mp4.go:580-591 (1-based chunk numbers): the last entry before the first one that
+        // starts at a later chunk. Same result as the reference's scan from the top, without its quadratic cost.
+        while (k < stsc.size() && stsc[k].first <= (uint32_t)(ci + 1)) k++;
+        const uint32_t per = k ? stsc[k - 1].second : 0;
         uint64_t off = chunk_offsets[ci];
         for (uint32_t it = 0; it < per && sample_idx < count; it++) {
             uint32_t sz = constant ? constant : sizes[(size_t)sample_idx];
@@ -212,10 +220,27 @@ struct alacb200_track {
 extern "C" {
 
 // FindALACTrack, mp4.go:233-300
+static int32_t find_alac_track(const uint8_t *file, uint64_t file_len, alacb200_track *t);
+
 int32_t alacb200_mp4_find_alac_track(const uint8_t *file, uint64_t file_len, alacb200_track **out) {
     if (!out) return ALACB200_E_ARG;
-    auto *t = new alacb200_track();
-    *out = t;
+    *out = nullptr;
+    alacb200_track *t = nullptr;
+    try {  // nothing may unwind through the C ABI
+        t = new alacb200_track();
+        *out = t;
+        return find_alac_track(file, file_len, t);
+    } catch (const std::exception &e) {
+        if (t) {
+            t->samples.clear();
+            t->cookie.clear();
+            try { t->error = std::string("mp4: ") + e.what(); } catch (...) {}
+        }
+        return ALACB200_E_NO_TRACK;
+    }
+}
+
+static int32_t find_alac_track(const uint8_t *file, uint64_t file_len, alacb200_track *t) {
     if (!file && file_len) {
         t->error = "null file image";
         return ALACB200_E_ARG;

@@ -141,6 +141,41 @@ def test_mp4_error_paths(pkg):
         pkg.FindALACTrack(data[:j] + b'xtco' + data[j + 4:])
 
 
+def test_mp4_parser_survives_mutations(pkg):
+    """The container parser is host code that reads untrusted files: bit flips, overwritten size fields, truncations and
+    splices of valid containers must end in a table or in ErrNoTrack, never in a crash, and a table it does return must
+    be bounded by what the file declares (entries are validated again, against the file length, when they are read)."""
+    rng = np.random.default_rng(2024)
+    cookie = ol.make_cookie(ol.Config.make(), wrappers=1)
+    bases = [build_m4a(cookie, _packets(), **kw)[0] for kw in (dict(), dict(samples_per_chunk=3, co64=True), dict(qt_v1=True, moov_first=True),
+                                                                 dict(extra_trak=True), dict(mdat_large=True))]
+    ok = bad = 0
+    for it in range(600):
+        d = bytearray(bases[it % len(bases)])
+        kind = it % 4
+        if kind == 0:  # random byte flips
+            for _ in range(int(rng.integers(1, 8))):
+                d[int(rng.integers(0, len(d)))] ^= int(rng.integers(1, 256))
+        elif kind == 1:  # a 32-bit field (most of the file is box sizes / counts / offsets) gets an extreme value
+            i = int(rng.integers(0, len(d) - 4))
+            d[i:i + 4] = [b'\xff\xff\xff\xff', b'\x00\x00\x00\x00', b'\x7f\xff\xff\xff', b'\x00\x00\x00\x01'][int(rng.integers(0, 4))]
+        elif kind == 2:  # truncation
+            d = d[:int(rng.integers(0, len(d)))]
+        else:  # splice a piece of the file over another place
+            a, b2 = sorted(int(x) for x in rng.integers(0, len(d), size=2))
+            c = int(rng.integers(0, len(d)))
+            piece = d[a:b2][:64]
+            d[c:c + len(piece)] = piece
+        try:
+            got_cookie, samples = pkg.FindALACTrack(bytes(d))
+            ok += 1
+            assert len(got_cookie) <= len(d)
+            assert len(samples) <= 1 << 24
+        except pkg.ErrNoTrack:
+            bad += 1
+    assert ok > 50 and bad > 50, (ok, bad)
+
+
 def test_missing_library_fails_loudly(pkg, monkeypatch):
     """No silent fallback: without libalacb200.so the package refuses to import (and says how to build it)."""
     monkeypatch.setattr(pkg, 'LIB_PATH', os.path.join(ROOT, 'saprobe-alac_b200', 'does_not_exist.so'))

@@ -95,3 +95,43 @@ def test_synthetic_cases_are_well_formed_for_the_oracle():
             seen.add(ol.code(st))
     assert n_exotic > 200 and n_hostile > 300
     assert seen <= {0, 3, 4, 5, 6, 7, 9}, seen
+
+
+def test_oracle_under_address_sanitizer(tmp_path):
+    """The oracle compiled with AddressSanitizer + UBSan over the exotic and hostile suites (every packet and every output
+    buffer in an exact-size heap block): no access outside either, and the same status / byte count / PCM hash as the
+    regular build. The places where the Go reference would panic must come back as status 9, not as memory errors."""
+    import os, subprocess, synth_cases
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = tmp_path / 'probe.c'
+    probe.write_text('int main(void){return 0;}')
+    if subprocess.run(['gcc', '-fsanitize=address,undefined', '-o', str(tmp_path / 'probe'), str(probe)], capture_output=True).returncode != 0:
+        pytest.skip('no sanitizer runtime in this image')
+    exe = str(tmp_path / 'oracle_asan')
+    # signed overflow is defined here (-fwrapv, as in oracle/Makefile); the shift checks stay on: Go's shift semantics are explicit in the source
+    subprocess.run(['gcc', '-O1', '-g', '-fwrapv', '-fsanitize=address,undefined', '-fno-sanitize=signed-integer-overflow',
+                    '-fno-sanitize-recover=undefined', '-o', exe, os.path.join(root, 'tests', 'cpp', 'oracle_asan_driver.c'),
+                    os.path.join(root, 'oracle', 'alac_oracle.c'), '-lpthread'], check=True)
+    blob = tmp_path / 'cases.bin'
+    want = []
+    with open(blob, 'wb') as f:
+        def put(cfg, packets):
+            cookie = ol.make_cookie(cfg)
+            f.write(len(cookie).to_bytes(4, 'little') + cookie + len(packets).to_bytes(4, 'little'))
+            for p in packets:
+                f.write(len(p).to_bytes(4, 'little') + bytes(p))
+                st, pcm = ol.decode_packet(cfg, p)
+                h = 2166136261
+                for b in (pcm or b''):
+                    h = ((h ^ b) * 16777619) & 0xffffffff
+                want.append(f'{st} {len(pcm or b"")} {h}')
+        for name, cfg, packets in synth_cases.exotic_cases():
+            put(cfg, packets[:2])
+        for name, cfg, packets in synth_cases.hostile_cases(max_per_seed=10):
+            put(cfg, packets)
+    r = subprocess.run([exe, str(blob)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = r.stdout.split('\n')[:-1]
+    assert len(got) == len(want) and len(want) > 500
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, (bad[:5], [got[i] for i in bad[:3]], [want[i] for i in bad[:3]])
