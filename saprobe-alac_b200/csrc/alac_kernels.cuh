@@ -1063,10 +1063,14 @@ __device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, con
                 for (int k = 0; k < FB; k++)
                     reinterpret_cast<uint4 *>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
             } else {
-                const uint32_t nb = frames_here * FB;  // a multiple of 4 (FB is even)
+                const uint32_t nb = frames_here * FB;  // 24-bit pairs: a multiple of 4 only for an even number of frames
 #pragma unroll
-                for (int k = 0; k < 4 * FB; k++)
+                for (int k = 0; k < 4 * FB; k++) {
                     if ((uint32_t)(4 * k + 4) <= nb) reinterpret_cast<uint32_t *>(dst)[k] = ow[k];
+                    else
+                        for (int j = 0; j < 4; j++)
+                            if ((uint32_t)(4 * k + j) < nb) dst[4 * k + j] = (uint8_t)(ow[k] >> (8 * j));
+                }
             }
         }
     }
@@ -1090,10 +1094,14 @@ __device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint
         for (int k = 0; k < NW4; k++)
             reinterpret_cast<uint4 *>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
     } else {
-        const uint32_t nb = frames_here * fb;  // a multiple of 4 for a pair
+        const uint32_t nb = frames_here * fb;  // 24-bit pairs: a multiple of 4 only for an even number of frames
 #pragma unroll
-        for (int k = 0; k < 4 * NW4; k++)
+        for (int k = 0; k < 4 * NW4; k++) {
             if ((uint32_t)(4 * k + 4) <= nb) reinterpret_cast<uint32_t *>(dst)[k] = ow[k];
+            else
+                for (int j = 0; j < 4; j++)
+                    if ((uint32_t)(4 * k + j) < nb) dst[4 * k + j] = (uint8_t)(ow[k] >> (8 * j));
+        }
     }
 }
 
@@ -2048,7 +2056,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
         }
         // flush: the warp walks the 32 packet rows; the whole tile is written so the packet's slot is fully defined
         const uint32_t tile_frames = min(TL, cfg.frame_length - (uint32_t)s0);
-        const uint32_t limit = tile_frames * fb;  // multiple of 4
+        const uint32_t limit = tile_frames * fb;  // a multiple of 4 except, for odd frame sizes, in the packet's last tile
         for (uint32_t r = 0; r < 32u; r++) {
             const uint32_t p = group * 32u + r;
             if (p >= x.npackets) break;
@@ -2072,6 +2080,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
                 for (uint32_t w = lane; w < nvec * 4u; w += 32u) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
             }
             for (uint32_t w = nvec * 4u + lane; w < (limit >> 2); w += 32u) reinterpret_cast<uint32_t *>(dst)[w] = src[w];
+            if (lane < (limit & 3u)) dst[(limit & ~3u) + lane] = reinterpret_cast<const uint8_t *>(src)[(limit & ~3u) + lane];
         }
     }
 }

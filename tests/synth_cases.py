@@ -138,6 +138,24 @@ def exotic_cases():
     return out
 
 
+def frame_length_cases():
+    """Frame lengths around every granularity of the kernel (16-sample entropy batches, 32-sample ring slots, 8- and
+    16-frame emit rows) and the extremes, for mono / stereo / 3 and 6 channels: two full packets and a short last one
+    each, from a signal with silence and +-LSB passages (zero runs that end exactly at, or run across, those edges)."""
+    out = []
+    seed = 7000
+    for fl in (1, 2, 3, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 4095, 4097, 65536):
+        for ch, bits in ((1, 16), (2, 24), (3, 24), (6, 16), (2, 16)):
+            if fl == 65536 and ch > 2:
+                continue
+            seed += 1
+            cfg = ol.Config.make(bit_depth=bits, num_channels=ch, frame_length=fl, sample_rate=48000)
+            n = 2 * fl + max(1, fl // 3)
+            x = _sig(ch, n, bits, seed, 'silence_lsb' if seed % 2 else 'music')
+            out.append((f'fl{fl}_c{ch}_d{bits}', cfg, ol.encode_stream(cfg, x)))
+    return out
+
+
 def hostile_cases(max_per_seed=40):
     """Mutated packets: (name, cfg, [packets]). Statuses (incl. ST_REF_PANIC) must match the oracle."""
     out = []

@@ -83,6 +83,13 @@ def test_exotic_shapes(pkg):
         assert_parity(pkg, ocfg, packets, name)
 
 
+def test_frame_length_sweep(pkg):
+    """Frame lengths at and around the kernel's own granularities (16 / 32 samples, 8 / 16 frames), 1 and 65536."""
+    for name, ocfg, packets in synth_cases.frame_length_cases():
+        _, _, st = assert_parity(pkg, ocfg, packets, name)
+        assert (st == 0).all(), name
+
+
 def test_hostile_packets(pkg):
     """Truncated / bit-flipped / garbage packets: same status word as the oracle (incl. where the Go
     reference would panic), same PCM whenever the packet still decodes."""
