@@ -98,6 +98,7 @@ struct Slot {
     uint32_t *user_out_bytes = nullptr;
     int32_t *user_status = nullptr;
     uint32_t pending = 0;
+    uint64_t pcm_stride = 0;  // out_stride the gaps of `pcm` were last zeroed for
 };
 
 struct ProfEvents {
@@ -422,10 +423,12 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, co
         if (!s.packed.reserve(mis + span + 64) || !s.offsets.reserve((size_t)m * 8) || !s.sizes.reserve((size_t)m * 4) ||
             !s.out_bytes.reserve((size_t)m * 8) || !s.h_in.reserve((size_t)m * 12) || !s.h_out.reserve((size_t)m * 8))
             return ALACB200_E_NOMEM;
-        if ((size_t)m * out_stride > s.pcm.cap) {
+        if ((size_t)m * out_stride > s.pcm.cap || s.pcm_stride != out_stride) {
             if (!s.pcm.reserve((size_t)m * out_stride)) return ALACB200_E_NOMEM;
-            // the kernels never touch the gap between frame_bytes and out_stride: define it once
+            // the kernel never touches the gap between frame_bytes and out_stride, and the gap travels back with the
+            // slot: define it once per buffer and per stride (PCM of an earlier call must not show up in it)
             CU(cudaMemsetAsync(s.pcm.p, 0, s.pcm.cap, s.stream));
+            s.pcm_stride = out_stride;
         }
         uint64_t *ho = (uint64_t *)s.h_in.p;
         uint32_t *hs = (uint32_t *)(ho + m);

@@ -136,6 +136,43 @@ def test_unaligned_offsets_and_wide_stride(pkg):
     assert (out[:, dec.frame_bytes:] == 0).all()
 
 
+def test_strides_and_offsets_for_every_emit_path(pkg):
+    """out_stride = frame bytes + 0 / 4 / 8 / 12 / 20 (so packet slots are 16-, 8- or only 4-byte aligned) and packets at odd
+    byte offsets, for the shapes that take the live path (stereo), the direct tail (mono), the row tail (6 / 8 channels)
+    and the tile tail (3 channels, under-filled packets): the 128-bit store paths must fall back to narrower stores and
+    never put PCM outside a packet's frame bytes."""
+    for ch, bits, shift in ((2, 24, 1), (2, 16, 0), (1, 24, 1), (6, 16, 0), (8, 24, 1), (3, 24, 0), (2, 20, 0), (2, 32, 2)):
+        ocfg = ol.Config.make(bit_depth=bits, num_channels=ch, sample_rate=48000)
+        x = make_signal('silence_lsb', ch, 4096 * 3 + 999, bits, 48000, seed=60 + ch + bits)
+        packets = ol.encode_stream(ocfg, x, ol.PacketOpts.make(bytes_shifted=shift))
+        packets.append(ol.Writer(ocfg).element(0, x[:4096, 0].copy(), order=4, coefs=[60, -30, 10, 5]).end().bytes())  # under-filled
+        blob = bytearray(b'\xee' * 5)
+        offs, sizes = [], []
+        for i, p in enumerate(packets):
+            offs.append(len(blob))
+            sizes.append(len(p))
+            blob += p + b'\xdd' * (1 + i % 5)
+        blob += b'\0' * 64
+        packed = np.frombuffer(bytes(blob), dtype=np.uint8)
+        offs = np.array(offs, dtype=np.uint64)
+        sizes = np.array(sizes, dtype=np.uint32)
+        want, want_nb, want_st = ol.decode_batch(ocfg, packed, offs, sizes, nthreads=2)
+        dec = pkg.NewPacketDecoder(to_pkg_cfg(pkg, ocfg), 0)
+        try:
+            for extra in (0, 4, 8, 12, 20):
+                stride = (dec.frame_bytes + 3) // 4 * 4 + extra
+                canary = np.full((len(packets), stride), 0xA5, dtype=np.uint8)
+                out, nb, st = dec.decode_packed(packed, offs, sizes, out=canary, out_stride=stride)
+                assert np.array_equal(st, want_st) and np.array_equal(nb, want_nb), (ch, bits, extra)
+                for i in range(len(packets)):
+                    assert np.array_equal(out[i, :nb[i]], want[i, :nb[i]]), (ch, bits, extra, i)
+                    assert (out[i, nb[i]:dec.frame_bytes] == 0).all(), (ch, bits, extra, i)  # rest of the frame: zeros
+                    gap = out[i, dec.frame_bytes:]  # the gap carries no PCM: zeros (copied with the slot) or untouched
+                    assert ((gap == 0) | (gap == 0xA5)).all(), (ch, bits, extra, i, gap[:8].tolist())
+        finally:
+            dec.close()
+
+
 def test_decoder_read_seek_m4a(pkg):
     """NewDecoder/Read/Seek over an M4A (BASELINE configs[0] shape, shortened): conformance_test.go:282-292 (bit-for-bit
     vs source) and :343-421 (seek at 0/25/50/75 % equals the tail of the full decode)."""
