@@ -156,6 +156,46 @@ def frame_length_cases():
     return out
 
 
+def entropy_edge_cases():
+    """Shapes that stress the entropy stage's bookkeeping: cookie parameters at the edges (kb 0 / 1 / 22 / 23 / 31 /
+    255, mb and pb 0 / 255), digital silence of every length around the batch / ring-slot / stream sizes (one long zero
+    run per stream, escape-coded when it is long), single impulses at those edges, +-LSB noise (a run-length code after
+    nearly every sample) and loud clipping noise (escape codes), as full and as partial packets."""
+    out = []
+    seed = 9000
+    # cookie parameters x signal kinds
+    for pb, mb, kb in ((40, 10, 14), (40, 10, 0), (40, 10, 1), (40, 10, 2), (40, 10, 22), (40, 10, 23), (40, 10, 31), (40, 10, 255),
+                       (0, 10, 14), (255, 10, 14), (40, 0, 14), (40, 255, 14), (1, 1, 9), (255, 255, 255)):
+        for kind, bits in (('lsb', 24), ('silence_lsb', 16), ('loud', 16), ('white', 24)):
+            seed += 1
+            cfg = ol.Config.make(bit_depth=bits, num_channels=2, sample_rate=48000, pb=pb, mb=mb, kb=kb)
+            x = _sig(2, 4096 + 1234, bits, seed, kind)
+            out.append((f'ag_pb{pb}_mb{mb}_kb{kb}_{kind}{bits}', cfg, ol.encode_stream(cfg, x)))
+    # silence and impulses at the edges
+    for fl in (16, 17, 32, 33, 48, 4096, 65536):
+        cfg = ol.Config.make(bit_depth=16, num_channels=2, frame_length=fl, sample_rate=48000)
+        z = np.zeros((fl, 2), dtype=np.int64)
+        packets = [ol.encode_packet(cfg, z)]
+        for n in {1, min(fl, 15), min(fl, 16), min(fl, 17), fl - 1}:
+            if n > 0:
+                packets.append(ol.encode_packet(cfg, z[:n]))  # partial silent packets
+        for pos in {0, 1, 14, 15, 16, 17, 31, 32, fl // 2, fl - 2, fl - 1}:
+            if 0 <= pos < fl:
+                y = z.copy()
+                y[pos, 0] = 1000
+                y[pos, 1] = -3
+                packets.append(ol.encode_packet(cfg, y))
+        # long runs of zeros between two non-zero stretches: run lengths around 16 / 32 / 255 / 256 / 4095
+        for run in (15, 16, 17, 31, 32, 33, 255, 256, 257, 4000):
+            if run + 8 <= fl:
+                y = z.copy()
+                y[:4] = [[5, -5], [7, 1], [-2, 2], [1, 1]]
+                y[4 + run:4 + run + 4] = [[3, 3], [-1, -8], [2, 0], [9, 9]]
+                packets.append(ol.encode_packet(cfg, y))
+        out.append((f'silence_edges_fl{fl}', cfg, packets))
+    return out
+
+
 def hostile_cases(max_per_seed=40):
     """Mutated packets: (name, cfg, [packets]). Statuses (incl. ST_REF_PANIC) must match the oracle."""
     out = []

@@ -90,6 +90,13 @@ def test_frame_length_sweep(pkg):
         assert (st == 0).all(), name
 
 
+def test_entropy_edge_sweep(pkg):
+    """Cookie parameters at their edges, silence / impulses / long zero runs at every internal boundary, +-LSB and
+    clipping noise: the entropy stage's batches, freezes and flavour switches against the oracle."""
+    for name, ocfg, packets in synth_cases.entropy_edge_cases():
+        assert_parity(pkg, ocfg, packets, name)
+
+
 def test_hostile_packets(pkg):
     """Truncated / bit-flipped / garbage packets: same status word as the oracle (incl. where the Go
     reference would panic), same PCM whenever the packet still decodes."""

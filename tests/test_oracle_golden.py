@@ -74,7 +74,7 @@ def test_synthetic_cases_are_well_formed_for_the_oracle():
     reference's sentinels (or where it would panic), and the threaded batch driver equals packet-by-packet decoding."""
     import synth_cases
     n_exotic = n_hostile = 0
-    for name, cfg, packets in synth_cases.exotic_cases() + synth_cases.frame_length_cases():
+    for name, cfg, packets in synth_cases.exotic_cases() + synth_cases.frame_length_cases() + synth_cases.entropy_edge_cases():
         for p in packets:
             st, pcm = ol.decode_packet(cfg, p)
             assert (pcm is None) == (st != ol.OK), name
@@ -127,7 +127,7 @@ def test_oracle_under_address_sanitizer(tmp_path):
                 want.append(f'{st} {len(pcm or b"")} {h}')
         for name, cfg, packets in synth_cases.exotic_cases():
             put(cfg, packets[:2])
-        for name, cfg, packets in synth_cases.frame_length_cases():
+        for name, cfg, packets in synth_cases.frame_length_cases() + synth_cases.entropy_edge_cases():
             if cfg.frame_length <= 4097:
                 put(cfg, packets)
         for name, cfg, packets in synth_cases.hostile_cases(max_per_seed=10):

@@ -7,7 +7,7 @@ import synth_cases, oracle_lib as ol
 from alac_b200_loader import load_package
 pkg = load_package()
 want = sys.argv[1]
-for gen in (synth_cases.exotic_cases, synth_cases.frame_length_cases, synth_cases.hostile_cases):
+for gen in (synth_cases.exotic_cases, synth_cases.frame_length_cases, synth_cases.entropy_edge_cases, synth_cases.hostile_cases):
     for name, ocfg, packets in gen():
         if name != want: continue
         cfg = pkg.ParseMagicCookie(ol.make_cookie(ocfg)); dec = pkg.NewPacketDecoder(cfg, 0)
