@@ -26,7 +26,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libalacb200.so')
+# ALACB200_LIB: developer override (an experiment or `make dev` build of the same ABI, e.g. libalacb200_dev.so)
+LIB_PATH = os.environ.get('ALACB200_LIB') or os.path.join(_HERE, 'libalacb200.so')
 
 # ---- API results / status words (include/alac_b200.h) ----------------------------------------------
 OK = 0

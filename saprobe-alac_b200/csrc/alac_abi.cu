@@ -502,8 +502,9 @@ size_t alacb200_format_error(int32_t status, char *buf, size_t cap) {
 
 const char *alacb200_last_error(void) { return g_last_error.c_str(); }
 
-// Developer hook (not part of include/alac_b200.h): point the decode kernel's per-role clock64 counters at a
-// device buffer of n_ctas*8 u64 (or NULL to switch them off). Used by tools/role_cycles.py.
+#ifdef ALACB200_DEV
+// Developer hooks (only in the `make dev` build, not part of include/alac_b200.h): point the decode kernel's per-role
+// clock64 counters at a device buffer of n_ctas*16 u64 (or NULL to switch them off). Used by tools/role_cycles.py.
 int32_t alacb200_debug_flags(unsigned int flags) {
     CU(cudaMemcpyToSymbol(g_debug_flags, &flags, sizeof(flags)));
     return ALACB200_OK;
@@ -513,6 +514,7 @@ int32_t alacb200_debug_role_cycles(unsigned long long *d_buf) {
     CU(cudaMemcpyToSymbol(g_role_cycles, &d_buf, sizeof(d_buf)));
     return ALACB200_OK;
 }
+#endif
 
 int32_t alacb200_set_profiling(alacb200_decoder *dec, int enable) {
     if (!dec) return ALACB200_E_ARG;

@@ -143,11 +143,28 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-// backoff_ns > 0: sleep between polls, so a warp that is far ahead of its producer does not eat the issue slots of the
-// entropy warps sharing its SM sub-partition (a ring chunk takes ~8000 cycles to produce)
+// A waiting role warp must not eat the issue slots of the entropy warps that share its SM sub-partition (a ring chunk
+// takes ~8000 cycles to produce, a whole stream ~1 M): mbarrier.try_wait with a suspend-time hint parks the warp in
+// hardware until the phase completes or the hint expires, so the poll loop issues a handful of instructions per wait
+// instead of one poll every ~20 cycles (__nanosleep returned almost at once in the round-1 captures: 90 M polls on c2).
+#ifndef ALACB200_WAIT
+#define ALACB200_WAIT 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t backoff_ns = 0) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
+#if ALACB200_WAIT == 1
+    const uint32_t hint = backoff_ns ? 100000u : 2000u;  // ns the hardware may keep the warp suspended per try
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(hint)
+            : "memory");
+        if (done) break;
+    }
+#else
+    uint32_t ns = backoff_ns;
     for (;;) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -155,16 +172,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (backoff_ns) __nanosleep(backoff_ns);
+        if (backoff_ns) {
+            __nanosleep(ns);
+#if ALACB200_WAIT == 2
+            ns = min(ns * 2u, 8000u);  // exponential back-off
+#endif
+        }
     }
+#endif
 }
 
-// Optional role timing (clock64 per role, lane 0): [cta][16] (8..10 = emit tail per warp), E total, E wait-empty, E top-up, P0 total, P0 wait,
-// P1 total, P1 wait, unused. Enabled by pointing g_role_cycles at a buffer (alacb200_debug_role_cycles).
-__device__ unsigned long long *g_role_cycles = nullptr;
 __device__ unsigned int g_sm_ticket[256];        // per-SM CTA counter (monotonic; only its value mod 4 is used)
 __device__ unsigned int g_sm_entropy_load[256];  // per SM: four 8-bit counts of resident entropy warps, by sub-partition
-__device__ unsigned int g_debug_flags = 0;  // bit 0: no live emission (developer experiments)
+// Developer build only (-DALACB200_DEV, `make dev`): per-role clock64 counters, [cta][16] (0..2 E total / wait-empty /
+// top-up, 3..4 P0, 5..6 P1, 8..10 emit tail per warp, 12..13 EMIT), enabled by pointing g_role_cycles at a buffer
+// (alacb200_debug_role_cycles), and g_debug_flags (bit 0: no live emission). The product library carries none of it.
+#ifdef ALACB200_DEV
+__device__ unsigned long long *g_role_cycles = nullptr;
+__device__ unsigned int g_debug_flags = 0;
 struct RoleTimer {
     unsigned long long *slot;
     unsigned long long acc[3] = {0, 0, 0};
@@ -176,6 +201,15 @@ struct RoleTimer {
     __device__ __forceinline__ void add(int k, unsigned long long t0) { if (slot) acc[k] += clock64() - t0; }
     __device__ __forceinline__ void flush(int n) { if (slot) for (int k = 0; k < n; k++) slot[k] = acc[k]; }
 };
+#else
+struct RoleTimer {
+    static constexpr unsigned long long *slot = nullptr;
+    __device__ __forceinline__ RoleTimer(uint32_t, int) {}
+    __device__ __forceinline__ unsigned long long now() const { return 0ull; }
+    __device__ __forceinline__ void add(int, unsigned long long) {}
+    __device__ __forceinline__ void flush(int) {}
+};
+#endif
 
 // ---- geometry of one decode CTA ---------------------------------------------------------------------
 // 4 warps, 32 packets: the ENTROPY warp hands residual codes, 32 samples at a time, through a shared-memory ring to
@@ -812,7 +846,12 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         s0.shift_bitpos = s1.shift_bitpos = 0;
         s0.u_first_slot = s1.u_first_slot = 0;
         // 2-channel streams whose 32 packets all carry one compressed pair: the V predictor warp emits PCM itself
-        const bool live_round = cfg.num_channels == 2u && !(g_debug_flags & 1u) &&
+        #ifdef ALACB200_DEV
+        const bool live_allowed = !(g_debug_flags & 1u);
+#else
+        const bool live_allowed = true;
+#endif
+        const bool live_round = cfg.num_channels == 2u && live_allowed &&
                                 __all_sync(FULL_MASK, !valid || (h.have && h.stereo && !h.escape && st == ST_OK &&
                                                                  (h.num[1] == 0 || h.num[1] == 31 || h.num[1] == 8 ||
                                                                   (h.num[1] >= 4 && h.num[1] <= 6))));
@@ -911,12 +950,14 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     BitReader::wait_all();
     rt.add(0, t_start);
     rt.flush(3);
+#ifdef ALACB200_DEV
     if (rt.slot) {
         uint32_t smid, wid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
         rt.slot[11] = ((unsigned long long)smid << 8) | wid;
     }
+#endif
     // tell both predictor warps to leave
     for (int cons = 0; cons < 2; cons++) {
         const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
@@ -1228,6 +1269,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
                         while ((u_seen = sm.u_chunks_done) < u_first_slot + ck + 1u) __nanosleep(64);
                         __threadfence_block();
                     }
+                    __syncwarp();  // orders every lane's reads of the parked samples after lane 0's acquire
                     u_seen = __shfl_sync(FULL_MASK, u_seen, 0);
                 }
                 live_prefetch(sm, lane, lc, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
@@ -2134,6 +2176,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
     if (lane == 0) atomicOr(&sm.subpart_mask, 1u << (hw_warp & 3u));
     __syncthreads();
     const uint32_t role = ((sm.subpart_mask == 0xfu ? hw_warp : warp) - sm.rotation) & 3u;
+#ifdef ALACB200_DEV
     if (g_role_cycles != nullptr && lane == 0) {  // developer aid: hardware warp slot of every warp of the CTA, by CTA warp index
         uint32_t wid;
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
@@ -2143,6 +2186,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
             g_role_cycles[(size_t)blockIdx.x * 16 + 15] = clock64();
         }
     }
+#endif
     if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
     else if (role == 3) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
     else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
