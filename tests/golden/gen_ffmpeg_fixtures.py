@@ -55,6 +55,16 @@ CASES = [
     ('s24_stereo_white', 24, 2, 96000, 5000, 'white', {}),
     ('s16_stereo_loud', 16, 2, 44100, 9000, 'loud', {}),
     ('s16_51_silence_lsb', 16, 6, 48000, 12000, 'silence_lsb', {}),
+    # round 2: 24-bit for every channel count (the full {16, 24} x 11 rates x 1-8 channels matrix at 64+ packets per case is
+    # regenerated at test time, tests/golden/wide_matrix.py; these stay as the always-available committed pin)
+    ('s24_3ch', 24, 3, 48000, 5000, 'music', {}),
+    ('s24_4ch', 24, 4, 44100, 5000, 'music', {}),
+    ('s24_5ch', 24, 5, 88200, 5000, 'silence_lsb', {}),
+    ('s24_51', 24, 6, 96000, 9000, 'music', {}),
+    ('s24_61', 24, 7, 48000, 5000, 'loud', {}),
+    ('s24_71_silence_lsb', 24, 8, 48000, 12000, 'silence_lsb', {}),
+    ('s16_mono_silence_lsb_11k', 16, 1, 11025, 20000, 'silence_lsb', {}),
+    ('s24_mono_silence_lsb_176k', 24, 1, 176400, 20000, 'silence_lsb', {}),
 ]
 
 

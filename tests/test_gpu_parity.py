@@ -97,6 +97,59 @@ def test_entropy_edge_sweep(pkg):
         assert_parity(pkg, ocfg, packets, name)
 
 
+def test_wide_ffmpeg_matrix_gpu(pkg):
+    """The reference's conformance matrix ({16, 24} x 11 rates x 1-8 channels, conformance_test.go:573-628), FFmpeg-encoded
+    on this box: the CUDA path must return the source PCM bit for bit (FFmpeg's own decoder is checked in build())."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import wide_matrix
+    if not wide_matrix.ffmpeg_available():
+        pytest.skip('FFmpeg libraries not importable on this box; the committed ffmpeg_fixtures.npz remains the pin')
+    npk = 0
+    for case in wide_matrix.wide_cases():
+        cookie, packets, x = wide_matrix.build(case)
+        cfg = pkg.ParseMagicCookie(cookie)
+        dec = pkg.NewPacketDecoder(cfg, 0)
+        try:
+            assert dec.Format() == pkg.PCMFormat(case['rate'], case['bits'], case['channels'])
+            packed, offs, sizes = pkg.pack_packets(packets)
+            out, nb, st = dec.decode_packed(packed, offs, sizes)
+        finally:
+            dec.close()
+        assert (st == 0).all(), case['name']
+        got = b''.join(bytes(out[i, :nb[i]]) for i in range(len(packets)))
+        assert got == ol.int_to_pcm_bytes(x, case['bits']), case['name']
+        npk += len(packets)
+    assert npk > 3000
+
+
+def test_synth_hashes_pin_the_gpu(pkg):
+    """The committed drift pin (tests/golden/synth_hashes.json: status word, byte count and PCM of every synthetic case
+    as recorded from the cross-checked oracle) against the CUDA path directly -- not via today's oracle build."""
+    import synth_pin
+    pin = synth_pin.load_pin()['cases']
+    other_input, bad, n = [], [], 0
+    decs = {}
+    try:
+        for name, ocfg, packets in synth_pin.all_cases():
+            if synth_pin.packets_digest(ocfg, packets) != pin[name]['packets_sha256']:
+                other_input.append(name)
+                continue
+            key = bytes(ol.make_cookie(ocfg))
+            if key not in decs:
+                decs[key] = pkg.NewPacketDecoder(pkg.ParseMagicCookie(key), 0)
+            packed, offs, sizes = pkg.pack_packets(packets)
+            out, nb, st = decs[key].decode_packed(packed, offs, sizes)
+            n += 1
+            if synth_pin.result_digest(st, nb, out) != pin[name]['result_sha256']:
+                bad.append(name)
+    finally:
+        for d in decs.values():
+            d.close()
+    assert not bad, f'GPU output differs from the committed pin on {len(bad)} cases: {bad[:5]}'
+    assert n > 400 and len(other_input) <= len(pin) // 20, (n, other_input[:5])
+
+
 def test_hostile_packets(pkg):
     """Truncated / bit-flipped / garbage packets: same status word as the oracle (incl. where the Go
     reference would panic), same PCM whenever the packet still decodes."""

@@ -97,6 +97,51 @@ def test_synthetic_cases_are_well_formed_for_the_oracle():
     assert seen <= {0, 3, 4, 5, 6, 7, 9}, seen
 
 
+def test_wide_ffmpeg_matrix_oracle():
+    """The reference's own conformance matrix (conformance_test.go:573-628: {16, 24} x 11 rates x 1-8 channels; here 64
+    packets + a partial one at three of the rates, 3 packets at the others), FFmpeg-encoded on the spot:
+    oracle == FFmpeg-decode == source, bit for bit, and the format metadata of the cookie (conformance_test.go:267-279)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import wide_matrix
+    if not wide_matrix.ffmpeg_available():
+        pytest.skip('FFmpeg libraries (opencv_python_headless.libs) not importable here; ffmpeg_fixtures.npz remains the pin')
+    npk = 0
+    for case in wide_matrix.wide_cases():
+        cookie, packets, x = wide_matrix.build(case)
+        st, cfg = ol.parse_cookie(cookie)
+        assert st == ol.OK and (cfg.bit_depth, cfg.num_channels, cfg.sample_rate) == (case['bits'], case['channels'], case['rate'])
+        packed, offs, sizes = ol.pack(packets)
+        out, nb, status = ol.decode_batch(cfg, packed, offs, sizes, nthreads=4)
+        assert (status == 0).all(), case['name']
+        got = b''.join(bytes(out[i, :nb[i]]) for i in range(len(packets)))
+        assert got == ol.int_to_pcm_bytes(x, case['bits']), case['name']
+        npk += len(packets)
+    assert npk > 3000
+
+
+def test_synth_hashes_pin_the_oracle():
+    """Drift pin for the restatement-only cases (20/32-bit, mode != 0, odd orders, DSE/FIL, hostile statuses ...): the
+    oracle's status word, byte count and PCM of every synthetic case must equal tests/golden/synth_hashes.json, recorded
+    when the oracle was cross-checked (gen_synth_hashes.py). The GPU suite asserts the same table, so kernel and oracle
+    cannot drift together. A case whose generated INPUT differs from the recorded one (the seeded signals go through
+    libm; another CPU may round one sample differently) is not judged; there must be next to none of them."""
+    import synth_pin
+    pin = synth_pin.load_pin()['cases']
+    cases = synth_pin.all_cases()
+    assert {n for n, _, _ in cases} == set(pin), 'case list changed: regenerate tests/golden/synth_hashes.json and say why'
+    other_input, bad = [], []
+    for name, cfg, packets in cases:
+        if synth_pin.packets_digest(cfg, packets) != pin[name]['packets_sha256']:
+            other_input.append(name)
+            continue
+        st, nb, out = synth_pin.oracle_result(cfg, packets)
+        if synth_pin.result_digest(st, nb, out) != pin[name]['result_sha256']:
+            bad.append(name)
+    assert not bad, f'oracle output drifted on {len(bad)} cases: {bad[:5]}'
+    assert len(other_input) <= len(cases) // 20, f'{len(other_input)} cases generate other inputs here: {other_input[:5]}'
+
+
 def test_oracle_under_address_sanitizer(tmp_path):
     """The oracle compiled with AddressSanitizer + UBSan over the exotic and hostile suites (every packet and every output
     buffer in an exact-size heap block): no access outside either, and the same status / byte count / PCM hash as the
