@@ -53,7 +53,11 @@ enum {
     /* Deviations (documented in DESIGN.md): */
     ALACB200_ST_REF_PANIC = 9,           /* the Go reference would PANIC on this packet (slice/index out of
                                             range); reported as a decode error */
-    ALACB200_ST_UNSUPPORTED_CONFIG = 10  /* channels not in 1..8 or frame length not in 1..65536 */
+    ALACB200_ST_UNSUPPORTED_CONFIG = 10, /* channels not in 1..8 or frame length not in 1..65536 */
+    /* Not a decode error: the packet's (offset, size) lies outside the bytes handed over, so nothing was read or
+     * decoded. The reference fails at this point in its READER (io.ReadFull -> "reading sample N: unexpected EOF",
+     * decode.go:172-174), before the packet decoder is involved; the host wrappers raise that error. */
+    ALACB200_ST_IO_TRUNCATED = 11
 };
 enum { ALACB200_CTX_NONE = 0, ALACB200_CTX_SCE = 1, ALACB200_CTX_CPE = 2, ALACB200_CTX_DSE = 3, ALACB200_CTX_FIL = 4 };
 enum { ALACB200_ENT_NONE = 0, ALACB200_ENT_MONO = 1, ALACB200_ENT_U = 2, ALACB200_ENT_V = 3 };
@@ -103,27 +107,75 @@ int32_t alacb200_get_config(const alacb200_decoder *dec, alacb200_config *out);
 uint64_t alacb200_max_packet_pcm_bytes(const alacb200_decoder *dec);
 
 /* DecodePackets (new, north star) == n x PacketDecoder.DecodePacket, decoder.go:117-128, on HOST buffers.
- *   packed            all packets; packet i is packed[offsets[i] .. offsets[i]+sizes[i])
+ *   packed            the bytes the packets live in: a packed buffer, or a whole M4A file image with the
+ *                     sample table (internal/mp4 SampleInfo, mp4.go:28-31) as offsets/sizes -- no re-packing
+ *   packed_bytes      bytes readable at `packed`; a packet with offsets[i]+sizes[i] > packed_bytes is not
+ *                     read and gets ALACB200_ST_IO_TRUNCATED
+ *   packet i          packed[offsets[i] .. offsets[i]+sizes[i]), any alignment, any order
  *   pcm_out           packet i's PCM goes to pcm_out + i*out_stride; out_stride >= max_packet_pcm_bytes
  *                     and a multiple of 4
  *   out_bytes[i]      numSamples*numChannels*bps on success (partial last packet => shorter), else 0
  *   status[i]         status word
- * Host buffers may be pageable or pinned (alacb200_pinned_alloc); pinned buffers are copied
- * asynchronously and overlap with the kernels. Inputs are borrowed for the call only
+ * Host buffers may be pageable or pinned (alacb200_pinned_alloc / alacb200_arena); pinned buffers are
+ * copied asynchronously and overlap with the kernels. Inputs are borrowed for the call only
  * (bits.Reset copies, bitbuffer.go:44). One call at a time per decoder; several decoders per
  * device are fine. */
-int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, const uint64_t *offsets,
-                                const uint32_t *sizes, uint32_t n, uint8_t *pcm_out, uint64_t out_stride,
-                                uint32_t *out_bytes, int32_t *status);
+int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, uint64_t packed_bytes,
+                                const uint64_t *offsets, const uint32_t *sizes, uint32_t n, uint8_t *pcm_out,
+                                uint64_t out_stride, uint32_t *out_bytes, int32_t *status);
+
+/* Decoder-owned pinned staging for the host wrappers (the Go shim's DecodePackets packs [][]byte into *in and
+ * reads the PCM from *out): grow-only, valid until the next alacb200_arena call or alacb200_destroy, so a
+ * steady stream of DecodePacket / DecodePackets calls allocates nothing (decoder.go:79-87 keeps its scratch
+ * the same way). */
+int32_t alacb200_arena(alacb200_decoder *dec, uint64_t in_bytes, uint64_t out_bytes, uint8_t **in, uint8_t **out);
 
 /* Same on DEVICE buffers (everything already resident in HBM), enqueued on `stream` (a cudaStream_t,
- * NULL = default stream) without synchronising. d_packed must be 16-byte aligned and readable for
+ * NULL = default stream) as ONE kernel launch without synchronising (the scratch is stream-ordered
+ * memory sized by the resident CTAs, not by n). d_packed must be 16-byte aligned and readable for
  * packed_bytes rounded up to 16. The decoder's scratch is shared, so calls on one decoder must be
- * stream-ordered. */
+ * stream-ordered; passing a different stream than the previous call first waits for that one. */
 int32_t alacb200_decode_packets_device(alacb200_decoder *dec, const uint8_t *d_packed, uint64_t packed_bytes,
                                        const uint64_t *d_offsets, const uint32_t *d_sizes, uint32_t n,
                                        uint8_t *d_pcm_out, uint64_t out_stride, uint32_t *d_out_bytes,
                                        int32_t *d_status, void *stream);
+
+/* ---- several tracks, several devices (BASELINE configs[4]: a library of mixed 16/24-bit tracks) -----------
+ * A PacketDecoder holds ONE cookie (decoder.go:79-87); a library batch mixes cookies. A library handle owns one
+ * pipeline per device and decodes any mix of tracks in one call: every track is checked like
+ * ParseMagicCookie + NewPacketDecoder, tracks are split into contiguous ranges balanced by compressed bytes
+ * over the devices (one submitting host thread per device, no collective), grouped by config inside a device
+ * so every kernel launch is depth-homogeneous, and cut into pipeline chunks that may span tracks. The bytes
+ * of a track are read in place (`data` = packed packets or the M4A file image, offsets/sizes = its sample
+ * table); pin them (alacb200_pinned_alloc) for asynchronous copies. */
+typedef struct alacb200_track_desc {
+    /* in */
+    const uint8_t *cookie;   /* magic cookie of the track (with or without the frma/alac wrappers) */
+    size_t cookie_len;
+    const uint8_t *data;     /* bytes the packets live in */
+    uint64_t data_len;
+    const uint64_t *offsets; /* sample table, n entries */
+    const uint32_t *sizes;
+    uint32_t n;
+    uint32_t reserved;
+    uint8_t *pcm_out;        /* packet i -> pcm_out + i*out_stride */
+    uint64_t out_stride;     /* >= frame_length*channels*bps of THIS track, multiple of 4 */
+    uint32_t *out_bytes;     /* n entries */
+    int32_t *status;         /* n entries */
+    /* out */
+    alacb200_config config;  /* the parsed cookie */
+    int32_t track_status;    /* ALACB200_ST_OK, or why the track has no decoder (INVALID_COOKIE ... BIT_DEPTH) */
+    int32_t result;          /* ALACB200_OK, ALACB200_E_CONFIG (see track_status), ALACB200_E_ARG, or a device error */
+    int32_t device;          /* CUDA device the track was decoded on (-1: not decoded) */
+    int32_t reserved2;
+} alacb200_track_desc;
+typedef struct alacb200_library alacb200_library;
+int32_t alacb200_library_create(const int *devices, int ndevices, alacb200_library **out);
+void alacb200_library_destroy(alacb200_library *lib);
+int32_t alacb200_library_devices(const alacb200_library *lib);
+/* Returns ALACB200_OK when every decodable track was decoded (per-track outcomes are in the descriptors), or
+ * the first device error. One call at a time per library. */
+int32_t alacb200_library_decode_tracks(alacb200_library *lib, alacb200_track_desc *tracks, uint32_t ntracks);
 
 /* Pinned (page-locked) host memory for packed input / PCM output. */
 void *alacb200_pinned_alloc(size_t bytes);
@@ -141,9 +193,7 @@ int32_t alacb200_device_count(void);
 /* Per-kernel device timing (CUDA events on the launch stream), for bench.py's roofline line. */
 typedef struct alacb200_profile {
     uint64_t launches_decode;   /* alac_decode_kernel launches since enable (stages 1-3 are one kernel) */
-    uint64_t launches_emit;     /* reserved: 0 (stage 3 runs as the tail of alac_decode_kernel) */
     double ms_decode;           /* summed event time of alac_decode_kernel */
-    double ms_emit;             /* reserved: 0 */
 } alacb200_profile;
 int32_t alacb200_set_profiling(alacb200_decoder *dec, int enable); /* enabling resets the counters */
 int32_t alacb200_get_profile(alacb200_decoder *dec, alacb200_profile *out); /* synchronises the recorded events */

@@ -1,15 +1,17 @@
-// alac_abi.cu -- the C ABI of include/alac_b200.h over the kernels in alac_kernels.cuh.
+// alac_abi.cu -- the C ABI of include/alac_b200.h over the kernel in alac_kernels.cuh.
 //
-// Host-side plumbing only: handles, device buffers, the chunked H2D -> decode kernel -> D2H pipeline over
-// four slots (a CUDA stream and its buffers each), pinned memory, error text. No decode arithmetic lives
-// here and there is no CPU fallback: if CUDA is unusable every decode entry point fails.
+// Host-side plumbing only: handles, device buffers, the chunked H2D -> decode kernel -> D2H pipeline over four slots (a
+// CUDA stream and its buffers each), the multi-track / multi-device front end, pinned memory, error text. No decode
+// arithmetic lives here and there is no CPU fallback: if CUDA is unusable every decode entry point fails.
 #include "alac_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/alac_b200.h"
@@ -30,28 +32,30 @@ bool cuda_ok(cudaError_t e, const char *what) {
         if (!cuda_ok((call), #call)) return ALACB200_E_CUDA; \
     } while (0)
 
-constexpr int kSlots = 4;  // pipeline depth of the host-buffer path
+constexpr int kSlots = 4;                         // pipeline depth of the host-buffer path
+constexpr uint32_t kMaxChunkPackets = 16384;      // packets per pipeline chunk
+constexpr uint64_t kMaxChunkPcm = 512ull << 20;   // PCM bytes per pipeline chunk
 
+// Stream-ordered device buffer: growing frees and allocates on the owning stream, so nothing in flight loses its
+// memory and the device is never synchronised. Contents are not preserved.
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
-    // grow-only; contents are not preserved
-    bool reserve(size_t bytes) {
+    bool reserve(size_t bytes, cudaStream_t stream) {
         if (bytes <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) {
-            g_last_error = "cudaMalloc failed";
+        release(stream);
+        const size_t want = bytes + bytes / 8 + 256;
+        if (cudaMallocAsync(&p, want, stream) != cudaSuccess) {
+            g_last_error = "cudaMallocAsync failed";
             cudaGetLastError();
+            p = nullptr;
             return false;
         }
         cap = want;
         return true;
     }
-    void release() {
-        if (p) cudaFree(p);
+    void release(cudaStream_t stream) {
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr;
         cap = 0;
     }
@@ -61,13 +65,12 @@ struct PinBuf {
     size_t cap = 0;
     bool reserve(size_t bytes) {
         if (bytes <= cap) return true;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        release();
+        const size_t want = bytes + bytes / 8 + 256;
         if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
             g_last_error = "cudaHostAlloc failed";
             cudaGetLastError();
+            p = nullptr;
             return false;
         }
         cap = want;
@@ -80,46 +83,70 @@ struct PinBuf {
     }
 };
 
-// What one in-flight batch needs besides its inputs and outputs: the parked samples and the element lists.
+// What a launch needs besides its inputs and outputs: one slot of parked samples and element lists per RESIDENT CTA (the
+// kernel's CTAs are persistent and pull packet groups from a counter), so its size does not depend on the batch.
 struct Work {
-    DevBuf scratch;  // int32 [groups][channels][frame_length][32]
-    DevBuf descs;    // PacketDesc [n]
+    DevBuf scratch;                // int32 [ctas][channels][frame_length][32]
+    DevBuf descs;                  // PacketDesc [ctas][32]
+    uint32_t *counters = nullptr;  // {next group, CTAs done}; zero between launches (the kernel's last CTA re-zeroes them)
+    bool reserve(uint32_t ctas, size_t per_cta_scratch, cudaStream_t stream) {
+        if (!scratch.reserve((size_t)ctas * per_cta_scratch, stream) || !descs.reserve((size_t)ctas * 32u * sizeof(PacketDesc), stream))
+            return false;
+        if (!counters) {
+            if (cudaMallocAsync((void **)&counters, 2 * sizeof(uint32_t), stream) != cudaSuccess ||
+                cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), stream) != cudaSuccess) {
+                g_last_error = "cudaMallocAsync failed (group counters)";
+                cudaGetLastError();
+                counters = nullptr;
+                return false;
+            }
+        }
+        return true;
+    }
+    void release(cudaStream_t stream) {
+        scratch.release(stream);
+        descs.release(stream);
+        if (counters) cudaFreeAsync(counters, stream);
+        counters = nullptr;
+    }
+};
+
+// A run of packets of one track inside a pipeline chunk.
+struct Segment {
+    const uint8_t *src;  // host bytes the offsets are relative to (packed packets or a whole file image)
+    uint64_t src_len;    // bytes readable at src
+    const uint64_t *offsets;
+    const uint32_t *sizes;
+    uint32_t n;
+    uint8_t *pcm_out;  // host; packet i at pcm_out + i * out_stride
+    uint32_t *out_bytes;
+    int32_t *status;
+};
+
+// Where the per-packet results of a retired chunk go (caller arrays may be pageable: copying into them straight from
+// the stream would make every chunk synchronous).
+struct Scatter {
+    uint32_t *out_bytes;
+    int32_t *status;
+    uint32_t first, n;          // rows [first, first + n) of the chunk
+    std::vector<uint32_t> bad;  // rows whose packet lies outside the source bytes
 };
 
 struct Slot {
     cudaStream_t stream = nullptr;
     Work work;
-    DevBuf packed, offsets, sizes, pcm, out_bytes, status;
+    DevBuf packed, meta, pcm, results;
     PinBuf h_in;   // pinned staging of this chunk's rebased offsets (u64) + sizes (u32)
     PinBuf h_out;  // pinned staging of this chunk's out_bytes (u32) + status (i32)
     cudaEvent_t done = nullptr;
-    // where h_out goes once the chunk has finished (caller arrays may be pageable: copying into them straight
-    // from the stream would make every chunk synchronous)
-    uint32_t *user_out_bytes = nullptr;
-    int32_t *user_status = nullptr;
+    std::vector<Scatter> scatter;
     uint32_t pending = 0;
-    uint64_t pcm_stride = 0;  // out_stride the gaps of `pcm` were last zeroed for
+    uint64_t pcm_stride = 0, pcm_frame_bytes = 0;  // what the gaps of `pcm` were last zeroed for
 };
 
 struct ProfEvents {
     cudaEvent_t e0, e1;
 };
-
-}  // namespace
-
-struct alacb200_decoder {
-    alacb200_config cfg;
-    DevConfig dev_cfg;
-    int device;
-    uint64_t frame_bytes;
-    Work device_path_work;  // scratch of alacb200_decode_packets_device
-    Slot slots[kSlots];
-    bool profiling = false;
-    std::vector<ProfEvents> prof_events;
-    alacb200_profile prof{};
-};
-
-namespace {
 
 struct DeviceGuard {
     int prev = -1;
@@ -140,67 +167,323 @@ int32_t check_config(const alacb200_config *cfg) {
     return ALACB200_ST_OK;
 }
 
+// The part of a cookie the kernel needs, and the size of a decoded packet.
+struct Shape {
+    DevConfig dev;
+    uint64_t frame_bytes;
+    bool same_kernel_config(const Shape &o) const {
+        return dev.frame_length == o.dev.frame_length && dev.bit_depth == o.dev.bit_depth && dev.num_channels == o.dev.num_channels &&
+               dev.pb == o.dev.pb && dev.mb == o.dev.mb && dev.kb == o.dev.kb;
+    }
+};
+Shape make_shape(const alacb200_config &cfg, uint32_t num_sms) {
+    Shape s;
+    s.dev.frame_length = cfg.frame_length;
+    s.dev.bit_depth = cfg.bit_depth;
+    s.dev.num_channels = cfg.num_channels;
+    s.dev.bps = (uint32_t)alacb200_bytes_per_sample(cfg.bit_depth);
+    s.dev.pb = cfg.pb;
+    s.dev.mb = cfg.mb;
+    s.dev.kb = cfg.kb;
+    s.dev.num_sms = num_sms;
+    s.frame_bytes = (uint64_t)cfg.frame_length * cfg.num_channels * s.dev.bps;
+    return s;
+}
 
-// Enqueue the decode kernel for n device-resident packets on `stream`.
-int32_t launch(alacb200_decoder *dec, Work &work, const uint8_t *d_packed, const uint64_t *d_offsets,
-               const uint32_t *d_sizes, uint32_t n, uint8_t *d_pcm, uint64_t out_stride, uint32_t *d_out_bytes,
-               int32_t *d_status, cudaStream_t stream) {
-    if (n == 0) return ALACB200_OK;
-    const DevConfig &c = dec->dev_cfg;
-    // Bound the parked-sample scratch: very large batches (a library shard is millions of packets) run as a
-    // sequence of launches on the same stream, each reusing the scratch of the one before it.
-    const uint64_t per_group = (uint64_t)c.num_channels * c.frame_length * 32u * sizeof(int32_t);
-    const uint32_t max_groups = (uint32_t)std::max<uint64_t>(64, (8ull << 30) / per_group);
-    if ((n + 31u) / 32u > max_groups) {
-        for (uint32_t a = 0; a < n; a += max_groups * 32u) {
-            const uint32_t m = std::min(n - a, max_groups * 32u);
-            int32_t rc = launch(dec, work, d_packed, d_offsets + a, d_sizes + a, m, d_pcm + (size_t)a * out_stride, out_stride,
-                                d_out_bytes + a, d_status + a, stream);
+// One device: streams, staging and scratch of the chunked host path, shared by whatever configs are decoded on it.
+struct Pipeline {
+    int device = -1;
+    uint32_t num_sms = 148;
+    uint32_t max_ctas = 0;  // CTAs the device keeps resident (SMs x CTAs per SM): the grid never needs more
+    Slot slots[kSlots];
+    uint32_t next_slot = 0;
+    bool profiling = false;
+    std::vector<ProfEvents> prof_events;
+    alacb200_profile prof{};
+
+    int32_t init(int dev) {
+        device = dev;
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        num_sms = (uint32_t)sms;
+        CU(cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
+        int per_sm = 0;  // persistent CTAs: as many as the device keeps resident
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, alac_decode_kernel, DEC_THREADS, sizeof(DecShared)));
+        if (per_sm <= 0) {
+            g_last_error = "alac_decode_kernel does not fit on this device";
+            return ALACB200_E_CUDA;
+        }
+        max_ctas = (uint32_t)(per_sm * sms);
+        if (std::getenv("ALACB200_VERBOSE"))
+            std::fprintf(stderr, "alacb200: device %d, %d SMs x %d resident CTAs of %d threads, %zu B shared each\n", dev, sms, per_sm,
+                         DEC_THREADS, sizeof(DecShared));
+        for (auto &s : slots) {
+            CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        return ALACB200_OK;
+    }
+    void destroy() {  // call with the device current
+        cudaDeviceSynchronize();
+        for (auto &pe : prof_events) {
+            cudaEventDestroy(pe.e0);
+            cudaEventDestroy(pe.e1);
+        }
+        prof_events.clear();
+        for (auto &s : slots) {
+            s.work.release(s.stream);
+            s.packed.release(s.stream);
+            s.meta.release(s.stream);
+            s.pcm.release(s.stream);
+            s.results.release(s.stream);
+            s.h_in.release();
+            s.h_out.release();
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+            s.done = nullptr;
+            s.stream = nullptr;
+        }
+    }
+
+    // Enqueue the decode kernel for n device-resident packets on `stream`: ONE launch whatever n is.
+    int32_t launch(Work &work, const Shape &shape, const uint8_t *d_packed, const uint64_t *d_offsets, const uint32_t *d_sizes,
+                   uint32_t n, uint8_t *d_pcm, uint64_t out_stride, uint32_t *d_out_bytes, int32_t *d_status, cudaStream_t stream) {
+        if (n == 0) return ALACB200_OK;
+        const DevConfig &c = shape.dev;
+        const uint32_t groups = (n + 31u) / 32u;
+        // one scratch slot per CTA; very long frames (up to 65536 x 8 channels = 64 MB per slot) get fewer CTAs
+        const uint64_t per_cta = (uint64_t)c.num_channels * c.frame_length * 32u * sizeof(int32_t);
+        const uint32_t budget_ctas = (uint32_t)std::max<uint64_t>(8, (4ull << 30) / per_cta);
+        const uint32_t grid = std::min(groups, std::min(max_ctas, budget_ctas));
+        if (!work.reserve(grid, (size_t)per_cta, stream)) return ALACB200_E_NOMEM;
+        ProfEvents pe{};
+        if (profiling) {
+            CU(cudaEventCreate(&pe.e0));
+            CU(cudaEventCreate(&pe.e1));
+            CU(cudaEventRecord(pe.e0, stream));
+        }
+        alac_decode_kernel<<<grid, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
+                                                                             (PacketDesc *)work.descs.p, d_pcm, out_stride, d_out_bytes,
+                                                                             d_status, work.counters);
+        CU(cudaGetLastError());
+        if (profiling) {
+            CU(cudaEventRecord(pe.e1, stream));
+            prof_events.push_back(pe);
+            prof.launches_decode++;
+        }
+        return ALACB200_OK;
+    }
+
+    int32_t drain_profile() {
+        for (auto &pe : prof_events) {
+            CU(cudaEventSynchronize(pe.e1));
+            float a = 0;
+            CU(cudaEventElapsedTime(&a, pe.e0, pe.e1));
+            prof.ms_decode += a;
+            cudaEventDestroy(pe.e0);
+            cudaEventDestroy(pe.e1);
+        }
+        prof_events.clear();
+        return ALACB200_OK;
+    }
+
+    // Wait for the slot's chunk and hand its per-packet results to the caller.
+    int32_t retire(Slot &s) {
+        if (!s.pending) return ALACB200_OK;
+        CU(cudaEventSynchronize(s.done));
+        const uint32_t *ob = (const uint32_t *)s.h_out.p;
+        const int32_t *st = (const int32_t *)(ob + s.pending);
+        for (auto &sc : s.scatter) {
+            std::memcpy(sc.out_bytes, ob + sc.first, (size_t)sc.n * 4);
+            std::memcpy(sc.status, st + sc.first, (size_t)sc.n * 4);
+            for (uint32_t r : sc.bad) {  // the packet lies outside the source bytes: the reference's reader fails before decoding
+                sc.out_bytes[r] = 0;
+                sc.status[r] = ALACB200_ST_IO_TRUNCATED;
+            }
+        }
+        s.scatter.clear();
+        s.pending = 0;
+        return ALACB200_OK;
+    }
+    int32_t drain() {
+        for (auto &s : slots) {
+            const int32_t rc = retire(s);
             if (rc != ALACB200_OK) return rc;
         }
         return ALACB200_OK;
     }
-    const uint32_t groups = (n + 31u) / 32u;
-    const size_t scratch_bytes = (size_t)groups * c.num_channels * c.frame_length * 32u * sizeof(int32_t);
-    if (scratch_bytes > work.scratch.cap || (size_t)n * sizeof(PacketDesc) > work.descs.cap) {
-        // growing frees the old buffers: make sure nothing in flight still uses them
-        CU(cudaDeviceSynchronize());
-        if (!work.scratch.reserve(scratch_bytes) || !work.descs.reserve((size_t)n * sizeof(PacketDesc)))
-            return ALACB200_E_NOMEM;
+    // After a failed call: nothing may still be copying into the caller's buffers, no slot may keep pointers into them.
+    void abort_all() {
+        for (auto &s : slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.pending = 0;
+            s.scatter.clear();
+        }
     }
-    ProfEvents pe{};
-    if (dec->profiling) {
-        CU(cudaEventCreate(&pe.e0));
-        CU(cudaEventCreate(&pe.e1));
-        CU(cudaEventRecord(pe.e0, stream));
-    }
-    alac_decode_kernel<<<groups, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c,
-                                                                           (int32_t *)work.scratch.p,
-                                                                           (PacketDesc *)work.descs.p, d_pcm, out_stride,
-                                                                           d_out_bytes, d_status);
-    CU(cudaGetLastError());
-    if (dec->profiling) {
-        CU(cudaEventRecord(pe.e1, stream));
-        dec->prof_events.push_back(pe);
-        dec->prof.launches_decode++;
-    }
-    return ALACB200_OK;
-}
 
-int32_t drain_profile(alacb200_decoder *dec) {
-    for (auto &pe : dec->prof_events) {
-        CU(cudaEventSynchronize(pe.e1));
-        float a = 0;
-        CU(cudaEventElapsedTime(&a, pe.e0, pe.e1));
-        dec->prof.ms_decode += a;
-        cudaEventDestroy(pe.e0);
-        cudaEventDestroy(pe.e1);
+    // One pipeline chunk: H2D of every segment's byte span, the kernel, D2H of PCM and per-packet results. All segments
+    // share the kernel config and out_stride. Returns as soon as the work is enqueued.
+    int32_t submit_chunk(const Shape &shape, uint64_t out_stride, const Segment *segs, size_t nsegs) {
+        Slot &s = slots[next_slot];
+        next_slot = (next_slot + 1) % kSlots;
+        int32_t rc = retire(s);  // the slot's previous chunk (and its staging) is finished
+        if (rc != ALACB200_OK) return rc;
+        uint32_t m = 0;
+        for (size_t k = 0; k < nsegs; k++) m += segs[k].n;
+        if (m == 0) return ALACB200_OK;
+        // byte span of every segment inside its source, and where it lands in the device staging (alignment mod 16 kept)
+        struct Span {
+            uint64_t lo, hi, dev_pos;
+        };
+        std::vector<Span> spans(nsegs);
+        uint64_t pos = 0;
+        for (size_t k = 0; k < nsegs; k++) {
+            const Segment &g = segs[k];
+            uint64_t lo = UINT64_MAX, hi = 0;
+            for (uint32_t i = 0; i < g.n; i++) {
+                const uint64_t off = g.offsets[i], sz = g.sizes[i];
+                if (off > g.src_len || sz > g.src_len - off) continue;  // outside the source: not copied, not decoded
+                lo = std::min(lo, off);
+                hi = std::max(hi, off + sz);
+            }
+            if (hi < lo) lo = hi = 0;
+            pos = (pos + 15u) / 16u * 16u + (lo & 15u);
+            spans[k] = Span{lo, hi, pos};
+            pos += hi - lo;
+        }
+        if (!s.packed.reserve(pos + 64, s.stream) || !s.meta.reserve((size_t)m * 12, s.stream) || !s.results.reserve((size_t)m * 8, s.stream) ||
+            !s.h_in.reserve((size_t)m * 12) || !s.h_out.reserve((size_t)m * 8))
+            return ALACB200_E_NOMEM;
+        const bool has_gap = out_stride > shape.frame_bytes;
+        if ((size_t)m * out_stride > s.pcm.cap || (has_gap && (s.pcm_stride != out_stride || s.pcm_frame_bytes != shape.frame_bytes))) {
+            if (!s.pcm.reserve((size_t)m * out_stride, s.stream)) return ALACB200_E_NOMEM;
+            // the kernel never touches the gap between frame_bytes and out_stride, and the gap travels back with the
+            // slot: define it once per buffer and per shape (PCM of an earlier call must not show up in it)
+            if (has_gap) CU(cudaMemsetAsync(s.pcm.p, 0, s.pcm.cap, s.stream));
+            s.pcm_stride = out_stride;
+            s.pcm_frame_bytes = shape.frame_bytes;
+        }
+        uint64_t *ho = (uint64_t *)s.h_in.p;
+        uint32_t *hs = (uint32_t *)(ho + m);
+        uint32_t row = 0;
+        for (size_t k = 0; k < nsegs; k++) {
+            const Segment &g = segs[k];
+            Scatter sc{g.out_bytes, g.status, row, g.n, {}};
+            for (uint32_t i = 0; i < g.n; i++, row++) {
+                const uint64_t off = g.offsets[i], sz = g.sizes[i];
+                if (off > g.src_len || sz > g.src_len - off) {
+                    ho[row] = 0;
+                    hs[row] = 0;
+                    sc.bad.push_back(i);
+                } else {
+                    ho[row] = off - spans[k].lo + spans[k].dev_pos;
+                    hs[row] = g.sizes[i];
+                }
+            }
+            s.scatter.push_back(std::move(sc));
+            if (spans[k].hi > spans[k].lo)
+                CU(cudaMemcpyAsync((uint8_t *)s.packed.p + spans[k].dev_pos, g.src + spans[k].lo, spans[k].hi - spans[k].lo,
+                                   cudaMemcpyHostToDevice, s.stream));
+        }
+        CU(cudaMemcpyAsync(s.meta.p, ho, (size_t)m * 12, cudaMemcpyHostToDevice, s.stream));  // offsets[m] then sizes[m]
+        const uint64_t *d_off = (const uint64_t *)s.meta.p;
+        const uint32_t *d_sz = (const uint32_t *)(d_off + m);
+        uint32_t *d_ob = (uint32_t *)s.results.p;  // out_bytes[m] then status[m], one D2H copy
+        int32_t *d_st = (int32_t *)(d_ob + m);
+        rc = launch(s.work, shape, (const uint8_t *)s.packed.p, d_off, d_sz, m, (uint8_t *)s.pcm.p, out_stride, d_ob, d_st, s.stream);
+        if (rc != ALACB200_OK) return rc;
+        row = 0;
+        for (size_t k = 0; k < nsegs; k++) {
+            const Segment &g = segs[k];
+            if (g.n)
+                CU(cudaMemcpyAsync(g.pcm_out, (const uint8_t *)s.pcm.p + (size_t)row * out_stride,
+                                   (size_t)(g.n - 1) * out_stride + shape.frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+            row += g.n;
+        }
+        CU(cudaMemcpyAsync(s.h_out.p, d_ob, (size_t)m * 8, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        s.pending = m;
+        return ALACB200_OK;
     }
-    dec->prof_events.clear();
-    return ALACB200_OK;
-}
+};
 
 uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+bool stride_ok(uint64_t out_stride, uint64_t frame_bytes) { return out_stride >= frame_bytes && (out_stride & 3u) == 0; }
+
+// Packets per chunk so that copies of chunk k+1 / k-1 overlap the kernel of chunk k.
+uint32_t chunk_packets(uint64_t n, uint64_t out_stride) {
+    uint32_t nchunks_target = 6;
+    if (const char *env = std::getenv("ALACB200_CHUNKS")) nchunks_target = (uint32_t)std::max(1, std::atoi(env));  // tuning knob
+    uint64_t chunk = (n + nchunks_target - 1u) / nchunks_target;
+    chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 512u), kMaxChunkPackets);
+    while (chunk > 32u && chunk * out_stride > kMaxChunkPcm) chunk /= 2u;
+    return (uint32_t)((chunk + 31u) & ~31ull);
+}
+
+}  // namespace
+
+struct alacb200_decoder {
+    alacb200_config cfg;
+    Shape shape;
+    Pipeline pipe;
+    cudaStream_t device_path_stream = nullptr;  // stream device_path_work was last used (and is owned) on
+    Work device_path_work;                      // scratch of alacb200_decode_packets_device
+    PinBuf arena_in, arena_out;                 // alacb200_arena: decoder-owned pinned staging for the host wrappers
+};
+
+// Decoders of several tracks (any mix of cookies) on one or more devices of this process.
+struct alacb200_library {
+    std::vector<std::unique_ptr<Pipeline>> devs;
+};
+
+namespace {
+
+// The tracks `order` on one device: already grouped by kernel config (so every launch is depth-homogeneous, SURVEY.md
+// 8e), cut into pipeline chunks that may span several tracks.
+int32_t decode_tracks_on(Pipeline &pipe, alacb200_track_desc *tracks, const std::vector<Shape> &shapes, const std::vector<uint32_t> &order) {
+    DeviceGuard guard(pipe.device);
+    if (!guard.ok) return ALACB200_E_CUDA;
+    int32_t rc = ALACB200_OK;
+    std::vector<Segment> segs;
+    uint32_t in_chunk = 0;
+    const Shape *cur = nullptr;
+    uint64_t cur_stride = 0;
+    auto flush = [&]() -> int32_t {
+        int32_t r = ALACB200_OK;
+        if (in_chunk) r = pipe.submit_chunk(*cur, cur_stride, segs.data(), segs.size());
+        segs.clear();
+        in_chunk = 0;
+        return r;
+    };
+    for (uint32_t t : order) {
+        alacb200_track_desc &tr = tracks[t];
+        const Shape &sh = shapes[t];
+        if (cur && (!cur->same_kernel_config(sh) || cur_stride != tr.out_stride)) {
+            if ((rc = flush()) != ALACB200_OK) break;
+        }
+        cur = &sh;
+        cur_stride = tr.out_stride;
+        uint32_t limit = kMaxChunkPackets;
+        while (limit > 32u && (uint64_t)limit * tr.out_stride > kMaxChunkPcm) limit /= 2u;
+        for (uint32_t a = 0; a < tr.n && rc == ALACB200_OK;) {
+            const uint32_t take = std::min(tr.n - a, limit - std::min(limit, in_chunk));
+            if (take == 0) {
+                rc = flush();
+                continue;
+            }
+            segs.push_back(Segment{tr.data, tr.data_len, tr.offsets + a, tr.sizes + a, take, tr.pcm_out + (size_t)a * tr.out_stride,
+                                   tr.out_bytes + a, tr.status + a});
+            in_chunk += take;
+            a += take;
+        }
+        if (rc != ALACB200_OK) break;
+    }
+    if (rc == ALACB200_OK) rc = flush();
+    if (rc == ALACB200_OK) rc = pipe.drain();
+    if (rc != ALACB200_OK) pipe.abort_all();
+    return rc;
+}
 
 }  // namespace
 
@@ -266,60 +549,24 @@ int32_t alacb200_create(const alacb200_config *cfg, int device, alacb200_decoder
     if (!guard.ok) return ALACB200_E_CUDA;
     auto *dec = new alacb200_decoder();
     dec->cfg = *cfg;
-    dec->device = device;
-    dec->dev_cfg.frame_length = cfg->frame_length;
-    dec->dev_cfg.bit_depth = cfg->bit_depth;
-    dec->dev_cfg.num_channels = cfg->num_channels;
-    dec->dev_cfg.bps = (uint32_t)alacb200_bytes_per_sample(cfg->bit_depth);
-    dec->dev_cfg.pb = cfg->pb;
-    dec->dev_cfg.mb = cfg->mb;
-    dec->dev_cfg.kb = cfg->kb;
-    {
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-        dec->dev_cfg.num_sms = (uint32_t)sms;
-    }
-    dec->frame_bytes = (uint64_t)cfg->frame_length * cfg->num_channels * dec->dev_cfg.bps;
-    cudaError_t e = cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared));
-    if (!cuda_ok(e, "cudaFuncSetAttribute(alac_decode_kernel)")) {
+    const int32_t rc = dec->pipe.init(device);
+    if (rc != ALACB200_OK) {
+        dec->pipe.destroy();
         delete dec;
-        return ALACB200_E_CUDA;
+        return rc;
     }
-    for (auto &s : dec->slots) {
-        if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate") ||
-            !cuda_ok(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate")) {
-            alacb200_destroy(dec);
-            return ALACB200_E_CUDA;
-        }
-    }
+    dec->shape = make_shape(*cfg, dec->pipe.num_sms);
     *out = dec;
     return ALACB200_OK;
 }
 
 void alacb200_destroy(alacb200_decoder *dec) {
     if (!dec) return;
-    DeviceGuard guard(dec->device);
-    cudaDeviceSynchronize();
-    for (auto &pe : dec->prof_events) {
-        cudaEventDestroy(pe.e0);
-        cudaEventDestroy(pe.e1);
-    }
-    dec->device_path_work.scratch.release();
-    dec->device_path_work.descs.release();
-    for (auto &s : dec->slots) {
-        s.work.scratch.release();
-        s.work.descs.release();
-        s.packed.release();
-        s.offsets.release();
-        s.sizes.release();
-        s.pcm.release();
-        s.out_bytes.release();
-        s.status.release();
-        s.h_in.release();
-        s.h_out.release();
-        if (s.done) cudaEventDestroy(s.done);
-        if (s.stream) cudaStreamDestroy(s.stream);
-    }
+    DeviceGuard guard(dec->pipe.device);
+    dec->pipe.destroy();  // synchronises the device first
+    dec->device_path_work.release(nullptr);
+    dec->arena_in.release();
+    dec->arena_out.release();
     delete dec;
 }
 
@@ -337,7 +584,7 @@ int32_t alacb200_get_config(const alacb200_decoder *dec, alacb200_config *out) {
     return ALACB200_OK;
 }
 
-uint64_t alacb200_max_packet_pcm_bytes(const alacb200_decoder *dec) { return dec ? dec->frame_bytes : 0; }
+uint64_t alacb200_max_packet_pcm_bytes(const alacb200_decoder *dec) { return dec ? dec->shape.frame_bytes : 0; }
 
 int32_t alacb200_decode_packets_device(alacb200_decoder *dec, const uint8_t *d_packed, uint64_t packed_bytes,
                                        const uint64_t *d_offsets, const uint32_t *d_sizes, uint32_t n,
@@ -347,112 +594,169 @@ int32_t alacb200_decode_packets_device(alacb200_decoder *dec, const uint8_t *d_p
     if (!dec) return ALACB200_E_ARG;
     if (n == 0) return ALACB200_OK;
     if (!d_packed || !d_offsets || !d_sizes || !d_pcm_out || !d_out_bytes || !d_status) return ALACB200_E_ARG;
-    if (out_stride < dec->frame_bytes || (out_stride & 3u) || (((uintptr_t)d_pcm_out) & 3u) ||
-        (((uintptr_t)d_packed) & 15u)) {
+    if (!stride_ok(out_stride, dec->shape.frame_bytes) || (((uintptr_t)d_pcm_out) & 3u) || (((uintptr_t)d_packed) & 15u)) {
         g_last_error = "out_stride must be >= max_packet_pcm_bytes and a multiple of 4; d_packed 16-byte aligned";
         return ALACB200_E_ARG;
     }
-    DeviceGuard guard(dec->device);
+    DeviceGuard guard(dec->pipe.device);
     if (!guard.ok) return ALACB200_E_CUDA;
-    return launch(dec, dec->device_path_work, d_packed, d_offsets, d_sizes, n, d_pcm_out, out_stride, d_out_bytes,
-                  d_status, (cudaStream_t)stream);
+    // the scratch is stream-ordered memory: moving to another stream first waits for the work of the previous one
+    cudaStream_t st = (cudaStream_t)stream;
+    if (st != dec->device_path_stream && dec->device_path_work.scratch.p) {
+        CU(cudaStreamSynchronize(dec->device_path_stream));
+        dec->device_path_work.release(dec->device_path_stream);
+    }
+    dec->device_path_stream = st;
+    return dec->pipe.launch(dec->device_path_work, dec->shape, d_packed, d_offsets, d_sizes, n, d_pcm_out, out_stride, d_out_bytes,
+                            d_status, st);
 }
 
-int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, const uint64_t *offsets,
+int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, uint64_t packed_bytes, const uint64_t *offsets,
                                 const uint32_t *sizes, uint32_t n, uint8_t *pcm_out, uint64_t out_stride,
                                 uint32_t *out_bytes, int32_t *status) {
     if (!dec) return ALACB200_E_ARG;
     if (n == 0) return ALACB200_OK;
     if (!packed || !offsets || !sizes || !pcm_out || !out_bytes || !status) return ALACB200_E_ARG;
-    if (out_stride < dec->frame_bytes || (out_stride & 3u)) {
+    if (!stride_ok(out_stride, dec->shape.frame_bytes)) {
         g_last_error = "out_stride must be >= max_packet_pcm_bytes and a multiple of 4";
         return ALACB200_E_ARG;
     }
-    DeviceGuard guard(dec->device);
+    DeviceGuard guard(dec->pipe.device);
     if (!guard.ok) return ALACB200_E_CUDA;
-
-    // Chunk the batch so copies of chunk k+1 / k-1 overlap the kernels of chunk k.
-    uint32_t nchunks_target = 6;
-    if (const char *env = std::getenv("ALACB200_CHUNKS")) nchunks_target = (uint32_t)std::max(1, std::atoi(env));  // tuning knob
-    uint32_t chunk = (n + nchunks_target - 1u) / nchunks_target;
-    chunk = std::min(std::max(chunk, 512u), 16384u);
-    const uint64_t max_chunk_pcm = 512ull << 20;
-    while (chunk > 32u && (uint64_t)chunk * out_stride > max_chunk_pcm) chunk /= 2u;
-    chunk = (chunk + 31u) & ~31u;
-
-    // Whatever way this call ends, nothing may still be copying into the caller's buffers afterwards and no slot may
-    // keep pointers into the caller's arrays for a later call to write through.
-    struct Drain {
-        alacb200_decoder *d;
-        bool clean = false;  // every slot was retired: nothing in flight
-        ~Drain() {
-            for (auto &s : d->slots) {
-                if (!clean) cudaStreamSynchronize(s.stream);
-                s.pending = 0;
-                s.user_out_bytes = nullptr;
-                s.user_status = nullptr;
-            }
-        }
-    } drain{dec};
-
+    const uint32_t chunk = chunk_packets(n, out_stride);
     int32_t rc = ALACB200_OK;
-    uint32_t slot_idx = 0;
-    auto retire = [](Slot &s) -> bool {  // wait for the slot's chunk and hand its per-packet results to the caller
-        if (cudaEventSynchronize(s.done) != cudaSuccess) return false;
-        if (s.pending) {
-            const uint32_t *ob = (const uint32_t *)s.h_out.p;
-            std::memcpy(s.user_out_bytes, ob, (size_t)s.pending * 4);
-            std::memcpy(s.user_status, ob + s.pending, (size_t)s.pending * 4);
-            s.pending = 0;
-        }
-        return true;
-    };
-    for (uint32_t a = 0; a < n && rc == ALACB200_OK; a += chunk, slot_idx = (slot_idx + 1) % kSlots) {
-        const uint32_t b = std::min(n, a + chunk), m = b - a;
-        Slot &s = dec->slots[slot_idx];
-        if (!retire(s)) return ALACB200_E_CUDA;  // the slot's previous chunk (and its staging) is finished
-        // byte range of this chunk inside `packed`
-        uint64_t lo = UINT64_MAX, hi = 0;
-        for (uint32_t i = a; i < b; i++) {
-            lo = std::min(lo, offsets[i]);
-            hi = std::max(hi, offsets[i] + sizes[i]);
-        }
-        if (hi < lo) lo = hi = 0;
-        const uint32_t mis = (uint32_t)(lo & 15u);  // keep each packet's alignment relative to 16 bytes
-        const uint64_t span = hi - lo;
-        if (!s.packed.reserve(mis + span + 64) || !s.offsets.reserve((size_t)m * 8) || !s.sizes.reserve((size_t)m * 4) ||
-            !s.out_bytes.reserve((size_t)m * 8) || !s.h_in.reserve((size_t)m * 12) || !s.h_out.reserve((size_t)m * 8))
-            return ALACB200_E_NOMEM;
-        if ((size_t)m * out_stride > s.pcm.cap || s.pcm_stride != out_stride) {
-            if (!s.pcm.reserve((size_t)m * out_stride)) return ALACB200_E_NOMEM;
-            // the kernel never touches the gap between frame_bytes and out_stride, and the gap travels back with the
-            // slot: define it once per buffer and per stride (PCM of an earlier call must not show up in it)
-            CU(cudaMemsetAsync(s.pcm.p, 0, s.pcm.cap, s.stream));
-            s.pcm_stride = out_stride;
-        }
-        uint64_t *ho = (uint64_t *)s.h_in.p;
-        uint32_t *hs = (uint32_t *)(ho + m);
-        for (uint32_t i = 0; i < m; i++) ho[i] = offsets[a + i] - lo + mis;
-        std::memcpy(hs, sizes + a, (size_t)m * 4);
-        uint32_t *d_ob = (uint32_t *)s.out_bytes.p;  // out_bytes[m] then status[m], one D2H copy
-        int32_t *d_st = (int32_t *)(d_ob + m);
-        if (span) CU(cudaMemcpyAsync((uint8_t *)s.packed.p + mis, packed + lo, span, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.offsets.p, ho, (size_t)m * 8, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.sizes.p, hs, (size_t)m * 4, cudaMemcpyHostToDevice, s.stream));
-        rc = launch(dec, s.work, (const uint8_t *)s.packed.p, (const uint64_t *)s.offsets.p, (const uint32_t *)s.sizes.p, m,
-                    (uint8_t *)s.pcm.p, out_stride, d_ob, d_st, s.stream);
-        if (rc != ALACB200_OK) break;
-        CU(cudaMemcpyAsync(pcm_out + (size_t)a * out_stride, s.pcm.p, (size_t)(m - 1) * out_stride + dec->frame_bytes,
-                           cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaMemcpyAsync(s.h_out.p, d_ob, (size_t)m * 8, cudaMemcpyDeviceToHost, s.stream));
-        CU(cudaEventRecord(s.done, s.stream));
-        s.user_out_bytes = out_bytes + a;
-        s.user_status = status + a;
-        s.pending = m;
+    for (uint32_t a = 0; a < n && rc == ALACB200_OK; a += chunk) {
+        const uint32_t m = std::min(n - a, chunk);
+        const Segment seg{packed, packed_bytes, offsets + a, sizes + a, m, pcm_out + (size_t)a * out_stride, out_bytes + a, status + a};
+        rc = dec->pipe.submit_chunk(dec->shape, out_stride, &seg, 1);
     }
-    for (auto &s : dec->slots)
-        if (!retire(s)) return ALACB200_E_CUDA;
-    drain.clean = rc == ALACB200_OK;
+    if (rc == ALACB200_OK) rc = dec->pipe.drain();
+    if (rc != ALACB200_OK) dec->pipe.abort_all();
+    return rc;
+}
+
+int32_t alacb200_arena(alacb200_decoder *dec, uint64_t in_bytes, uint64_t out_bytes, uint8_t **in, uint8_t **out) {
+    if (!dec || !in || !out) return ALACB200_E_ARG;
+    DeviceGuard guard(dec->pipe.device);
+    if (!guard.ok) return ALACB200_E_CUDA;
+    if (!dec->arena_in.reserve((size_t)in_bytes + 64) || !dec->arena_out.reserve((size_t)out_bytes + 64)) return ALACB200_E_NOMEM;
+    *in = (uint8_t *)dec->arena_in.p;
+    *out = (uint8_t *)dec->arena_out.p;
+    return ALACB200_OK;
+}
+
+// ---- several tracks, several devices ----------------------------------------------------------------------------
+int32_t alacb200_library_create(const int *devices, int ndevices, alacb200_library **out) {
+    if (!out || ndevices < 1 || !devices) return ALACB200_E_ARG;
+    *out = nullptr;
+    const int ndev = alacb200_device_count();
+    auto lib = std::unique_ptr<alacb200_library>(new alacb200_library());
+    int32_t rc = ALACB200_OK;
+    for (int k = 0; k < ndevices && rc == ALACB200_OK; k++) {
+        if (ndev <= 0 || devices[k] < 0 || devices[k] >= ndev) {
+            g_last_error = "no usable CUDA device (this library has no CPU fallback)";
+            rc = ALACB200_E_NO_DEVICE;
+            break;
+        }
+        DeviceGuard guard(devices[k]);
+        if (!guard.ok) {
+            rc = ALACB200_E_CUDA;
+            break;
+        }
+        lib->devs.emplace_back(new Pipeline());
+        rc = lib->devs.back()->init(devices[k]);
+    }
+    if (rc != ALACB200_OK) {
+        alacb200_library_destroy(lib.release());
+        return rc;
+    }
+    *out = lib.release();
+    return ALACB200_OK;
+}
+
+void alacb200_library_destroy(alacb200_library *lib) {
+    if (!lib) return;
+    for (auto &p : lib->devs) {
+        DeviceGuard guard(p->device);
+        p->destroy();
+    }
+    delete lib;
+}
+
+int32_t alacb200_library_devices(const alacb200_library *lib) { return lib ? (int32_t)lib->devs.size() : 0; }
+
+int32_t alacb200_library_decode_tracks(alacb200_library *lib, alacb200_track_desc *tracks, uint32_t ntracks) {
+    if (!lib || (!tracks && ntracks)) return ALACB200_E_ARG;
+    // per track: ParseMagicCookie + NewPacketDecoder's checks (config.go:47-81, decoder.go:90-110)
+    std::vector<Shape> shapes(ntracks);
+    std::vector<uint64_t> weight(ntracks, 0);
+    std::vector<uint32_t> good;
+    for (uint32_t t = 0; t < ntracks; t++) {
+        alacb200_track_desc &tr = tracks[t];
+        tr.result = ALACB200_OK;
+        tr.device = -1;
+        tr.track_status = alacb200_parse_cookie(tr.cookie, tr.cookie_len, &tr.config);
+        if (tr.track_status == ALACB200_ST_OK) tr.track_status = check_config(&tr.config);
+        if (tr.track_status != ALACB200_ST_OK) {
+            tr.result = ALACB200_E_CONFIG;
+            continue;
+        }
+        shapes[t] = make_shape(tr.config, 0);
+        if (tr.n == 0) continue;
+        if (!tr.data || !tr.offsets || !tr.sizes || !tr.pcm_out || !tr.out_bytes || !tr.status || !stride_ok(tr.out_stride, shapes[t].frame_bytes)) {
+            tr.result = ALACB200_E_ARG;
+            continue;
+        }
+        for (uint32_t i = 0; i < tr.n; i++) weight[t] += tr.sizes[i];
+        good.push_back(t);
+    }
+    // contiguous track ranges per device, balanced by compressed bytes; inside a device, tracks grouped by config
+    const size_t nd = lib->devs.size();
+    uint64_t total = 0;
+    for (uint32_t t : good) total += weight[t];
+    std::vector<std::vector<uint32_t>> per_dev(nd);
+    uint64_t acc = 0;
+    for (uint32_t t : good) {
+        size_t d = total ? (size_t)(((long double)acc + weight[t] / 2.0L) * nd / (long double)total) : 0;
+        d = std::min(d, nd - 1);
+        per_dev[d].push_back(t);
+        tracks[t].device = lib->devs[d]->device;
+        acc += weight[t];
+    }
+    for (size_t d = 0; d < nd; d++) {
+        for (uint32_t t : per_dev[d]) shapes[t].dev.num_sms = lib->devs[d]->num_sms;
+        std::stable_sort(per_dev[d].begin(), per_dev[d].end(), [&](uint32_t a, uint32_t b) {
+            const DevConfig &x = shapes[a].dev, &y = shapes[b].dev;
+            if (x.bit_depth != y.bit_depth) return x.bit_depth < y.bit_depth;
+            if (x.num_channels != y.num_channels) return x.num_channels < y.num_channels;
+            if (x.frame_length != y.frame_length) return x.frame_length < y.frame_length;
+            if (x.pb != y.pb) return x.pb < y.pb;
+            if (x.mb != y.mb) return x.mb < y.mb;
+            return x.kb < y.kb;
+        });
+    }
+    std::vector<int32_t> rcs(nd, ALACB200_OK);
+    std::vector<std::string> errs(nd);
+    auto run = [&](size_t d) {
+        rcs[d] = decode_tracks_on(*lib->devs[d], tracks, shapes, per_dev[d]);
+        if (rcs[d] != ALACB200_OK) errs[d] = g_last_error;
+    };
+    if (nd == 1) {
+        run(0);
+    } else {  // one submitting host thread per device
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < nd; d++) th.emplace_back(run, d);
+        for (auto &x : th) x.join();
+    }
+    int32_t rc = ALACB200_OK;
+    for (size_t d = 0; d < nd; d++)
+        if (rcs[d] != ALACB200_OK) {
+            if (rc == ALACB200_OK) {
+                g_last_error = errs[d];
+                rc = rcs[d];
+            }
+            for (uint32_t t : per_dev[d]) tracks[t].result = rcs[d];
+        }
     return rc;
 }
 
@@ -482,6 +786,7 @@ const char *alacb200_strerror(int32_t status) {
     case ALACB200_ST_BIT_DEPTH: return "alac: unsupported bit depth";
     case ALACB200_ST_REF_PANIC: return "alac: malformed packet (the reference decoder would panic)";
     case ALACB200_ST_UNSUPPORTED_CONFIG: return "alac: unsupported channel count or frame length";
+    case ALACB200_ST_IO_TRUNCATED: return "unexpected EOF";
     default: return "alac: unknown status";
     }
 }
@@ -490,6 +795,7 @@ size_t alacb200_format_error(int32_t status, char *buf, size_t cap) {
     if (!buf || cap == 0) return 0;
     const int code = ALACB200_ST_CODE(status);
     if (code == ALACB200_ST_OK) return (size_t)std::snprintf(buf, cap, "ok");
+    if (code == ALACB200_ST_IO_TRUNCATED) return (size_t)std::snprintf(buf, cap, "unexpected EOF");  // io.ReadFull, decode.go:172-174
     const bool is_config = code == ALACB200_ST_INVALID_COOKIE || code == ALACB200_ST_UNSUPPORTED_VERSION ||
                            code == ALACB200_ST_BIT_DEPTH || code == ALACB200_ST_UNSUPPORTED_CONFIG;
     static const char *ctx[] = {"", "SCE/LFE: ", "CPE: ", "DSE: ", "FIL: "};
@@ -518,22 +824,22 @@ int32_t alacb200_debug_role_cycles(unsigned long long *d_buf) {
 
 int32_t alacb200_set_profiling(alacb200_decoder *dec, int enable) {
     if (!dec) return ALACB200_E_ARG;
-    DeviceGuard guard(dec->device);
+    DeviceGuard guard(dec->pipe.device);
     if (!guard.ok) return ALACB200_E_CUDA;
-    int32_t rc = drain_profile(dec);
+    int32_t rc = dec->pipe.drain_profile();
     if (rc != ALACB200_OK) return rc;
-    dec->profiling = enable != 0;
-    if (enable) dec->prof = alacb200_profile{};
+    dec->pipe.profiling = enable != 0;
+    if (enable) dec->pipe.prof = alacb200_profile{};
     return ALACB200_OK;
 }
 
 int32_t alacb200_get_profile(alacb200_decoder *dec, alacb200_profile *out) {
     if (!dec || !out) return ALACB200_E_ARG;
-    DeviceGuard guard(dec->device);
+    DeviceGuard guard(dec->pipe.device);
     if (!guard.ok) return ALACB200_E_CUDA;
-    int32_t rc = drain_profile(dec);
+    int32_t rc = dec->pipe.drain_profile();
     if (rc != ALACB200_OK) return rc;
-    *out = dec->prof;
+    *out = dec->pipe.prof;
     return ALACB200_OK;
 }
 

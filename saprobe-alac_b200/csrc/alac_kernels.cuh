@@ -212,10 +212,13 @@ struct RoleTimer {
 #endif
 
 // ---- geometry of one decode CTA ---------------------------------------------------------------------
-// 4 warps, 32 packets: the ENTROPY warp hands residual codes, 32 samples at a time, through a shared-memory ring to
-// two PREDICTOR warps: consumer 0 takes the mono / U stream of every element, consumer 1 the V stream; the EMIT warp
-// follows consumer 1's ring.
-constexpr int DEC_THREADS = 128;
+// 3 warps work on one group of 32 packets at a time (lane = packet); a CTA is persistent and pulls group after group
+// from a counter. The ENTROPY warp hands residual codes, 32 samples at a time, through two shared-memory rings to the
+// PREDICTOR warp: ring 0 carries the mono / U stream of every element, ring 1 the V stream (the streams of a packet
+// follow each other in the bitstream, so one predictor warp serves both rings in turn); the EMIT warp follows ring 1.
+constexpr int DEC_THREADS = 96;
+constexpr int DEC_WARPS = DEC_THREADS / 32;
+constexpr int CTAS_PER_SM = 5;   // 96 threads x 128 registers and ~42 KB of shared memory per CTA
 constexpr int RING_SLOTS = 2;    // ring depth per consumer
 constexpr int CHUNK = 32;        // samples per ring slot
 constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged per lane (512 B window)
@@ -229,23 +232,28 @@ struct DecShared {
     int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (16 KB)
     uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
                                              // live-emit word, shift bit position, first consumer-0 slot of the U stream
-    // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
-    int32_t live_u[CHUNK][32];
+    // live emission (2-channel streams): the shift bytes of the current 32-frame chunk
     uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
     // barriers last: stage 3 reuses everything in front of them as its transpose tiles
     uint64_t full_bar[2][RING_SLOTS];
-    uint64_t empty_bar[2][RING_SLOTS];  // consumer 1's slots are released by the V predictor warp AND the emit warp
-    uint64_t vdone_bar[RING_SLOTS];     // V predictor warp -> emit warp: the slot now holds decoded V samples
-    volatile uint32_t u_chunks_done;    // ring slots the U/mono predictor warp has finished and parked (release/acquire by fences)
-    uint32_t rotation;                  // sub-partition chosen for the entropy warp of this CTA
-    uint32_t subpart_mask;              // sub-partitions the four warps report
+    uint64_t empty_bar[2][RING_SLOTS];  // ring 1's slots are released by the predictor warp AND the emit warp
+    uint64_t vdone_bar[RING_SLOTS];     // predictor warp -> emit warp: the ring-1 slot now holds decoded V samples
+    volatile uint32_t u_chunks_done;    // ring-0 slots the predictor warp has finished and parked (release/acquire by fences)
+    uint32_t group;                     // packet group this CTA works on
+    uint32_t next_group;                // the one after it, fetched by the entropy warp while the group is decoded
+    uint32_t entropy_smsp;              // sub-partition of this CTA's entropy warp
+    uint32_t warp_smsp[DEC_WARPS];      // sub-partition every warp reports
+    uint32_t role_of_warp[DEC_WARPS];
 };
 static_assert(offsetof(DecShared, fifo) == 0 && FIFO_CHUNKS * 16 == 512, "lane windows must be 512-byte aligned");
 static_assert(offsetof(DecShared, ring) % 16 == 0 && offsetof(DecShared, live_shift) % 16 == 0 && offsetof(DecShared, full_bar) % 8 == 0, "alignment");
 
 
 // job meta word
-enum : uint32_t { JOB_INACTIVE = 0, JOB_REG = 1, JOB_GENERIC = 2, JOB_EXIT = 3 };
+enum : uint32_t { JOB_INACTIVE = 0, JOB_REG = 1, JOB_GENERIC = 2, JOB_EXIT = 3 };  // JOB_EXIT: the group is finished
+// warp-uniform flags in the meta word of a ring-0 job: a V stream follows on ring 1 / ring 1 carries the other half of
+// an interleaved escape pair (the one predictor warp has to know where its next stream arrives)
+enum : uint32_t { JOBF_V_FOLLOWS = 1u << 24, JOBF_PAIR = 1u << 25 };
 __device__ __forceinline__ uint32_t job_meta(uint32_t kind, uint32_t order, uint32_t den, uint32_t mode, uint32_t chan_bits,
                                              uint32_t slot) {
     return kind | (order << 2) | (den << 7) | ((mode != 0 ? 1u : 0u) << 11) | (chan_bits << 12) | (slot << 18);
@@ -573,8 +581,8 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
 // For an interleaved escape pair both consumers' slots are filled in the same pass.
 __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int cons, uint32_t *seq, const Packet &pk,
                                                const DevConfig &cfg, BitReader &br, uint32_t &bp, int32_t &st,
-                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, bool &quiet,
-                                               RoleTimer &rt) {
+                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, uint32_t flags,
+                                               bool &quiet, RoleTimer &rt) {
     bool active = sp.active && st == ST_OK;
     const uint32_t nmax = __reduce_max_sync(FULL_MASK, active ? sp.n : 0u);
     const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
@@ -602,7 +610,7 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
         }
         if (c == 0) {
             sm.job[cons][slot][0][lane] = sp.n;
-            sm.job[cons][slot][1][lane] = active ? sp.meta : (uint32_t)JOB_INACTIVE;
+            sm.job[cons][slot][1][lane] = (active ? sp.meta : (uint32_t)JOB_INACTIVE) | flags;
             sm.job[cons][slot][2][lane] = sp.coef_bitpos;
             sm.job[cons][slot][3][lane] = nmax;
             sm.job[cons][slot][4][lane] = active ? sp.live : 0u;
@@ -810,15 +818,20 @@ __device__ __forceinline__ void parse_to_next_element(const Packet &pk, const De
     }
 }
 
+// One group of 32 packets. `seq` (ring sequence numbers) lives across the groups of a persistent CTA; `descs` are the
+// CTA's own 32 descriptors.
 __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
                                              const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
                                              uint32_t npackets, const DevConfig &cfg, PacketDesc *__restrict__ descs,
-                                             uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status) {
-    const uint32_t pidx = blockIdx.x * 32u + lane;
+                                             uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status, uint32_t group,
+                                             uint32_t *seq, uint32_t *__restrict__ counters) {
+    // the group after this one: fetched now, read by the whole CTA after the group's barrier
+    if (lane == 0) sm.next_group = atomicAdd(&counters[0], 1u);
+    const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
-    PacketDesc *desc = descs + pidx;
+    PacketDesc *desc = descs + lane;
     const uint32_t fifo_addr = smem_u32(&sm.fifo[lane][0]) ^ ((lane & 7u) << 4);
 
     Cursor cur{0, false};
@@ -826,8 +839,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     int32_t st = ST_OK;
     bool parsing = valid;
     if (valid && pk.size > 0x0FFFFFFFu) { st = ST_REF_PANIC; parsing = false; }  // bit positions are 32-bit here
-    uint32_t seq[2] = {0, 0};
-    uint32_t u_first = 0;    // consumer-0 sequence number at which the current element's U / mono stream starts
+    uint32_t u_first = 0;    // ring-0 sequence number at which the current element's U / mono stream starts
     bool quiet = false;      // warp-uniform: run-length codes keep appearing, decode them in line (decode_batch<true>)
     BitReader br;
     br.fifo = fifo_addr;
@@ -884,6 +896,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         // compressed elements: pass 0 = U (or mono), pass 1 = V; escape pairs: pass 2, one interleaved sweep
         // feeding both consumers (decoder.go:513-533)
         uint32_t bp = cur.bp;
+        const bool v_follows = __any_sync(FULL_MASK, h.have && h.stereo && !h.escape);  // pass 1 will run
 #pragma unroll 1
         for (int pass = 0; pass < 3; pass++) {
             const bool esc_pair = h.have && h.stereo && h.escape;
@@ -906,7 +919,8 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                 a.shift_bitpos = h.shift_bitpos;
                 a.u_first_slot = u_first;
             }
-            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, quiet, rt);
+            const uint32_t flags = pass == 0 ? (v_follows ? (uint32_t)JOBF_V_FOLLOWS : 0u) : pass == 2 ? (uint32_t)JOBF_PAIR : 0u;
+            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, flags, quiet, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
                 if ((st & 0xff) == ST_REF_PANIC) st |= ctx;
                 else st |= ctx | ((pass == 1 ? ENT_V : h.stereo ? ENT_U : ENT_MONO) << 12);
@@ -958,12 +972,13 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         rt.slot[11] = ((unsigned long long)smid << 8) | wid;
     }
 #endif
-    // tell both predictor warps to leave
+    // the group is finished: tell the predictor warp (ring 0, then ring 1) and, through ring 1, the emit warp
     for (int cons = 0; cons < 2; cons++) {
         const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
         mbar_wait(&sm.empty_bar[cons][slot], par ^ 1u);
         sm.job[cons][slot][1][lane] = JOB_EXIT;
         mbar_arrive(&sm.full_bar[cons][slot]);
+        seq[cons]++;
     }
     if (valid) {
         desc->status = st;
@@ -1007,23 +1022,11 @@ struct LiveCtx {
     bool publish;  // U / mono predictor warp of a 2-channel stream: the emit warp reads its parked samples back
 };
 
-// Start fetching what the emission of chunk `ck` needs: the parked U samples of the 32 frames (one 4 KB block,
-// cooperative) and this lane's shift bytes, all by cp.async so they land while the predictor runs.
-__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const LiveCtx &lc, const Packet &pk, uint32_t ck,
-                                              bool live_lane, uint32_t n_lane, uint32_t sb, uint32_t shift_bitpos,
-                                              uint32_t &rel0) {
+// Start fetching what the emission of chunk `ck` needs besides the samples: this lane's shift bytes, by cp.async so they
+// land while the predictor runs.
+__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const Packet &pk, uint32_t ck, bool live_lane,
+                                              uint32_t n_lane, uint32_t sb, uint32_t shift_bitpos, uint32_t &rel0) {
     const uint32_t base_i = ck * CHUNK;
-    const uint8_t *ug = reinterpret_cast<const uint8_t *>(lc.u_base + (size_t)base_i * 32u);
-    const uint32_t frames_left = lc.frame_length > base_i ? lc.frame_length - base_i : 0u;
-    const uint32_t ubase = smem_u32(&sm.live_u[0][0]);
-#pragma unroll
-    for (uint32_t k = 0; k < 8; k++) {
-        const uint32_t piece = k * 32u + lane;                  // 16-byte piece of the 4 KB block: frame = piece / 8
-        const uint32_t nb = (piece >> 3) < frames_left ? 16u : 0u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ubase + piece * 16u),
-                     "l"(ug + (nb ? (size_t)piece * 16u : 0)), "r"(nb)
-                     : "memory");
-    }
     rel0 = 0;
     const uint32_t cnt = (live_lane && n_lane > base_i) ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
     if (sb && cnt) {
@@ -1049,8 +1052,9 @@ __device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, cons
     }
 }
 
-// Generic (any depth / shift) emission of the 32 frames of chunk `ck` of a live pair: V from live_v, U from live_u, shift bytes from live_shift;
-// two batches of 16 frames, each leaving as 2*BPS 128-bit stores to the lane's own packet slot (matrix.go:30-215).
+// Generic (any depth / shift) emission of the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from the
+// parked samples (loaded here: this is the cold path), shift bytes from live_shift; two batches of 16 frames, each
+// leaving as 2*BPS 128-bit stores to the lane's own packet slot (matrix.go:30-215).
 template <int BPS>
 __device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
@@ -1066,13 +1070,16 @@ __device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, con
         const uint32_t f0 = ck * CHUNK + half * EB;
         if (f0 >= lc.frame_length) break;
         const uint32_t cnt = n_lane > f0 ? min((uint32_t)EB, n_lane - f0) : 0u;
+        int32_t uv[EB];
+#pragma unroll
+        for (int q = 0; q < EB; q++) uv[q] = f0 + (uint32_t)q < lc.frame_length ? __ldcg(lc.u_base + (size_t)(f0 + q) * 32u + lane) : 0;
         uint32_t ow[4 * FB];
 #pragma unroll
         for (int k = 0; k < 4 * FB; k++) ow[k] = 0;
 #pragma unroll
         for (int q = 0; q < EB; q++) {
             const uint32_t jq = half * EB + (uint32_t)q;
-            int32_t left = sm.live_u[jq][lane], right = vsrc[jq * 32u];
+            int32_t left = uv[q], right = vsrc[jq * 32u];
             if (mix_res != 0) {  // matrix.go:40-41
                 const int32_t v = right;
                 left = left + v - sar_go(mix_res * v, mix_bits);
@@ -1146,14 +1153,14 @@ __device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint
     }
 }
 
-// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u, shift bytes from live_shift; two
-// batches of 16 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
+// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from registers (uv), shift bytes from live_shift;
+// two batches of 16 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
 // The two shapes real streams have -- 16-bit, and 24-bit with one shifted byte -- are packed with byte permutes
 // (3 PRMT per 2 frames); everything else takes the generic path.
 template <int BPS>
 __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
-                                          const int32_t *vsrc) {
+                                          const int32_t *vsrc, const int32_t (&uv)[CHUNK]) {
     const bool fast = (BPS == 2 && lc.bit_depth == 16) || (BPS == 3 && lc.bit_depth == 24 && sb == 8u);
     if (!__all_sync(FULL_MASK, fast)) {
         live_emit_generic<BPS>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
@@ -1162,8 +1169,8 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
     const int32_t mix_res = (int32_t)(int8_t)((live_word >> 8) & 0xffu);
     const uint32_t mix_bits = live_word & 0xffu;
     const uint32_t *shrow = reinterpret_cast<const uint32_t *>(&sm.live_shift[lane][0]);
-#pragma unroll 1
-    for (uint32_t half = 0; half < 2; half++) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {  // unrolled: uv is indexed statically
         const uint32_t f0 = ck * CHUNK + half * 16u;
         if (f0 >= lc.frame_length) break;
         const uint32_t cnt = n_lane > f0 ? min(16u, n_lane - f0) : 0u;
@@ -1183,9 +1190,9 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int q = 2 * pr + e;
-                    const uint32_t jq = half * 16u + (uint32_t)q;
+                    const int jq = half * 16 + q;
                     int32_t left, right;
-                    unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
+                    unmix(uv[jq], vsrc[jq * 32], mix_res, mix_bits, left, right);
                     // (x << 8) | shift byte (matrix.go:132-135): frame 2k sits in the upper half of S[k], 2k+1 in the lower
                     uint32_t l24 = __byte_perm(S[pr], (uint32_t)left, e == 0 ? 0x6543 : 0x6541);
                     uint32_t r24 = __byte_perm(S[pr], (uint32_t)right, e == 0 ? 0x6542 : 0x6540);
@@ -1202,9 +1209,9 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
             uint32_t ow[16];
 #pragma unroll
             for (int q = 0; q < 16; q++) {
-                const uint32_t jq = half * 16u + (uint32_t)q;
+                const int jq = half * 16 + q;
                 int32_t left, right;
-                unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
+                unmix(uv[jq], vsrc[jq * 32], mix_res, mix_bits, left, right);
                 uint32_t w = __byte_perm((uint32_t)left, (uint32_t)right, 0x5410);
                 if ((uint32_t)q >= cnt) w = 0;
                 ow[q] = w;
@@ -1214,21 +1221,22 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
     }
 }
 
-// EMIT warp (2-channel streams): follows consumer 1's ring behind the V predictor warp. For a live stream it turns every
-// slot (decoded V samples) plus the parked U samples and the shift bytes into interleaved PCM in pcm_out; for any other
-// stream it only hands the slot back. It is the last reader of consumer 1's slots.
+// EMIT warp (2-channel streams): follows ring 1 behind the predictor warp. For a live stream it turns every slot (decoded
+// V samples) plus the parked U samples and the shift bytes into interleaved PCM in pcm_out; for any other stream it only
+// hands the slot back. It is the last reader of ring 1's slots. `seq` / `u_seen` live across the groups of the CTA.
 __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
                                           const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
                                           uint32_t npackets, const DevConfig &cfg, const int32_t *__restrict__ scratch,
-                                          PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out, uint64_t out_stride) {
-    const uint32_t pidx = blockIdx.x * 32u + lane;
+                                          PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out, uint64_t out_stride,
+                                          uint32_t group, uint32_t &seq, uint32_t &u_seen) {
+    const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     LiveCtx lc;
-    lc.u_base = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u;  // slot 0 = U
+    lc.u_base = scratch;  // slot 0 of the CTA's scratch = U
     lc.slot = pcm_out + (size_t)pidx * out_stride;
-    lc.desc = descs + pidx;
+    lc.desc = descs + lane;
     lc.frame_length = cfg.frame_length;
     lc.bps = cfg.bps;
     lc.bit_depth = cfg.bit_depth;
@@ -1236,8 +1244,6 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
     lc.enabled = true;
     RoleTimer rt(lane, 12);
     const unsigned long long t_start = rt.now();
-    uint32_t seq = 0;
-    uint32_t u_seen = 0;  // consumer-0 ring slots known to be parked (acquired)
 #pragma unroll 1
     for (;;) {
         // first slot of a stream: its job
@@ -1246,7 +1252,11 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
         mbar_wait(&sm.vdone_bar[slot], par, 400);
         rt.add(1, tw);
         const uint32_t meta = sm.job[1][slot][1][lane];
-        if ((meta & 3u) == JOB_EXIT) break;
+        if ((meta & 3u) == JOB_EXIT) {  // the group is finished: hand the slot back and leave
+            mbar_arrive(&sm.empty_bar[1][slot]);
+            seq++;
+            break;
+        }
         const uint32_t n = sm.job[1][slot][0][lane];
         const uint32_t nmax = __shfl_sync(FULL_MASK, sm.job[1][slot][3][lane], 0);
         const uint32_t live_word = sm.job[1][slot][4][lane];
@@ -1262,8 +1272,9 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
             slot = seq % RING_SLOTS;
             par = (seq / RING_SLOTS) & 1u;
             uint32_t rel0 = 0;
+            int32_t uv[CHUNK];  // the parked U samples of this chunk's 32 frames
             if (live_any) {
-                // the U predictor warp must have parked chunk ck of this pair's U stream (it normally did long ago)
+                // the predictor warp must have parked chunk ck of this pair's U stream (it normally did long ago)
                 if (u_seen < u_first_slot + ck + 1u) {  // warp-uniform; one acquire covers everything published before it
                     if (lane == 0) {
                         while ((u_seen = sm.u_chunks_done) < u_first_slot + ck + 1u) __nanosleep(64);
@@ -1272,7 +1283,12 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
                     __syncwarp();  // orders every lane's reads of the parked samples after lane 0's acquire
                     u_seen = __shfl_sync(FULL_MASK, u_seen, 0);
                 }
-                live_prefetch(sm, lane, lc, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
+                // U: one coalesced 128-byte line per frame, straight into registers (they land while V is predicted)
+                const uint32_t base_i = ck * CHUNK;
+                const int32_t *up = lc.u_base + (size_t)base_i * 32u + lane;
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) uv[j] = base_i + (uint32_t)j < lc.frame_length ? __ldcg(up + j * 32) : 0;
+                live_prefetch(sm, lane, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
             }
             if (ck > 0) {
                 tw = rt.now();
@@ -1283,9 +1299,9 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncwarp();
                 const int32_t *vsrc = &sm.ring[1][slot][0][lane];
-                if (cfg.bps == 3) live_emit<3>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
-                else if (cfg.bps == 2) live_emit<2>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
-                else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+                if (cfg.bps == 3) live_emit<3>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc, uv);
+                else if (cfg.bps == 2) live_emit<2>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc, uv);
+                else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc, uv);
                 __syncwarp();
             }
             mbar_arrive(&sm.empty_bar[1][slot]);
@@ -1305,6 +1321,17 @@ __device__ __forceinline__ void publish_parked(DecShared &sm, uint32_t lane, uin
         __threadfence_block();  // writer and reader share the CTA (and the SM's path to L2, which the reader's cp.async.cg takes)
         sm.u_chunks_done = seq;
     }
+}
+
+// sign-extend the low `bits` (1..32) of v: (v << (32 - bits)) >> (32 - bits) in one SGXT
+__device__ __forceinline__ int32_t sext_bits(int32_t v, uint32_t bits) {
+    int32_t r;
+    asm("bfe.s32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(bits));
+    return r;
+}
+// if (p) c += a * b, as one predicated IMAD
+__device__ __forceinline__ void mad_if(int32_t &c, int32_t a, int32_t b, bool p) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q mad.lo.s32 %0, %1, %2, %0;\n\t}" : "+r"(c) : "r"(a), "r"(b), "r"((uint32_t)p));
 }
 
 // Register predictor: orders 4/5/6/8 with int32 coefficients (unpcBlock4/5/6/8, predictor.go:99-618), plus
@@ -1342,6 +1369,17 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
     int32_t dprev = 0;
     int32_t *outp = dst;
     const uint32_t nchunks = max(1u, (jb.nmax + CHUNK - 1) / CHUNK);
+    // From the second ring slot on every FIR lane is past its warm-up (order <= 8 < 32). If the warp carries nothing but
+    // such lanes, with samples of at most 31 bits (so a history difference never is INT_MIN) and no pre-pass, the
+    // steady-state body below runs instead of the general one: no warm-up arithmetic, and the early-exit ladder of
+    // predictor.go:137-185 in a sign-folded form -- with E = del0 for a positive residual and ~del0 for a negative one,
+    // both ladders are "E -= weight * q; go on while E >= thr", q = |diff| >> denShift rounded down / up, thr = 1 / 0.
+#ifdef ALACB200_NO_STEADY
+    const bool steady_ok = false;
+#else
+    const bool steady_ok = !MODE && __all_sync(FULL_MASK, !active || (fir_order && jb.chan_bits <= 31u));
+#endif
+    const uint32_t den_mask = (1u << den) - 1u;
 #pragma unroll 1
     for (uint32_t ck = 0; ck < nchunks; ck++) {
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
@@ -1352,6 +1390,48 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
         }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
         int32_t *vdst = &sm.ring[cons][slot][0][lane];
+        if (steady_ok && ck > 0) {
+            int32_t *const out_end = dst + (size_t)n_lane * 32u;
+#pragma unroll 2
+            for (uint32_t j = 0; j < CHUNK; j++) {
+                const uint32_t code = (uint32_t)src[j * 32];
+                const int32_t r = code_to_residual(code);
+                int32_t top;
+                if (T == 8) top = sel4 ? h[4] : sel5 ? h[5] : sel6 ? h[6] : h[8];
+                else top = sel4 ? h[4] : sel5 ? h[5] : h[6];
+                int32_t d[T];
+                int32_t sum = den_half;
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    d[t] = top - h[t];
+                    if (t >= 4) d[t] &= (int32_t)tmask[t];  // orders start at 4: taps 0..3 always live
+                    sum -= c[t] * d[t];
+                }
+                const int32_t x = sext_bits(r + top + (sum >> den), jb.chan_bits);
+                const int32_t smask = r >> 31;                       // 0 / -1
+                const int32_t nsone = -(smask | 1);                  // -1 for r > 0, +1 for r < 0: coef -= sign(diff) * sign(r)
+                const uint32_t bias = (uint32_t)smask & den_mask;    // round |diff| >> den up for r < 0
+                const int32_t thr = smask + 1;
+                int32_t E = r ^ smask;
+                bool alive = r != 0;
+#pragma unroll
+                for (int t = T - 1; t >= 0; t--) {
+                    const int32_t sg = max(min(d[t], 1), -1);        // signOfInt
+                    mad_if(c[t], sg, nsone, alive);
+                    if (t > 0) {
+                        const uint32_t q = ((uint32_t)(sg * d[t]) + bias) >> den;  // |diff| < 2^31: no wrap
+                        E -= wgt[t] * (int32_t)q;
+                        alive = alive && (E >= thr);                 // masked taps: q = 0, E unchanged
+                    }
+                }
+#pragma unroll
+                for (int t = T; t > 0; t--) h[t] = h[t - 1];
+                h[0] = x;
+                if (LIVE) vdst[j * 32] = x;
+                else if (outp < out_end) *outp = x;
+                outp += 32;
+            }
+        } else {
 // unroll 2, not more: the entropy warps sharing the SM pay for every extra KB of hot code in instruction fetch
 #pragma unroll 2
         for (uint32_t j = 0; j < CHUNK; j++) {
@@ -1401,6 +1481,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
             if (LIVE) vdst[j * 32] = x;
             else if (i < n_lane) *outp = x;
             outp += 32;
+        }
         }
         if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
         mbar_arrive(&sm.empty_bar[cons][slot]);
@@ -1479,73 +1560,157 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
     }
 }
 
-__device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, int cons, const uint8_t *__restrict__ packed,
+// The two halves of an interleaved escape pair (decoder.go:513-533) arrive on both rings in lock step; the raw samples
+// are only parked (order 0, no pre-pass), slot by slot, ring 0 then ring 1. The first ring-0 slot is already full.
+__device__ __forceinline__ void stream_escape_pair(DecShared &sm, uint32_t lane, uint32_t *seq, const Job &j0, bool act0,
+                                                   int32_t *__restrict__ dst0, bool valid, const DevConfig &cfg,
+                                                   int32_t *__restrict__ scratch_lane, bool publish, RoleTimer &rt) {
+    const uint32_t nchunks = max(1u, (j0.nmax + CHUNK - 1) / CHUNK);
+    uint32_t n1 = 0;
+    int32_t *dst1 = scratch_lane;
+#pragma unroll 1
+    for (uint32_t ck = 0; ck < nchunks; ck++) {
+        {
+            const uint32_t slot = seq[0] % RING_SLOTS, par = (seq[0] / RING_SLOTS) & 1u;
+            if (ck > 0) mbar_wait(&sm.full_bar[0][slot], par, 200);
+            const int32_t *src = &sm.ring[0][slot][0][lane];
+            const uint32_t n0 = act0 ? j0.n : 0u;
+#pragma unroll 4
+            for (uint32_t j = 0; j < CHUNK; j++) {
+                const uint32_t i = ck * CHUNK + j;
+                if (i < n0) dst0[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
+            }
+            mbar_arrive(&sm.empty_bar[0][slot]);
+            seq[0]++;
+            if (publish && ((seq[0] & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq[0]);
+        }
+        {
+            const uint32_t slot = seq[1] % RING_SLOTS, par = (seq[1] / RING_SLOTS) & 1u;
+            const unsigned long long tw = rt.now();
+            mbar_wait(&sm.full_bar[1][slot], par, 200);
+            rt.add(1, tw);
+            if (ck == 0) {  // the job of the pair's second half
+                const uint32_t meta = sm.job[1][slot][1][lane];
+                const bool act1 = valid && (meta & 3u) != JOB_INACTIVE;
+                n1 = act1 ? sm.job[1][slot][0][lane] : 0u;
+                dst1 = scratch_lane + (size_t)((meta >> 18) & 7u) * cfg.frame_length * 32u;
+            }
+            const int32_t *src = &sm.ring[1][slot][0][lane];
+#pragma unroll 4
+            for (uint32_t j = 0; j < CHUNK; j++) {
+                const uint32_t i = ck * CHUNK + j;
+                if (i < n1) dst1[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
+            }
+            mbar_arrive(&sm.vdone_bar[slot]);
+            mbar_arrive(&sm.empty_bar[1][slot]);
+            seq[1]++;
+        }
+    }
+}
+
+// The first slot of the next stream on ring `cons` is full: read its job. Returns the meta word.
+__device__ __forceinline__ uint32_t read_job(DecShared &sm, int cons, uint32_t slot, uint32_t lane, Job &jb) {
+    jb.n = sm.job[cons][slot][0][lane];
+    const uint32_t meta = sm.job[cons][slot][1][lane];
+    jb.coef_bitpos = sm.job[cons][slot][2][lane];
+    jb.nmax = __shfl_sync(FULL_MASK, sm.job[cons][slot][3][lane], 0);
+    jb.live = sm.job[cons][slot][4][lane];
+    jb.shift_bitpos = sm.job[cons][slot][5][lane];
+    jb.u_first_slot = sm.job[cons][slot][6][lane];
+    jb.kind = meta & 3u;
+    jb.order = (meta >> 2) & 31u;
+    jb.den = (meta >> 7) & 15u;
+    jb.mode = (meta >> 11) & 1u;
+    jb.chan_bits = (meta >> 12) & 63u;
+    jb.slot = (meta >> 18) & 7u;
+    return meta;
+}
+
+// One stream of ring `cons`, by the loop that fits the orders / modes the warp's lanes carry.
+__device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk, const Job &jb,
+                                           bool active, int32_t *__restrict__ dst, RoleTimer &rt, const LiveCtx &lc) {
+    const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
+    const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
+    const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
+    // live emission (2-channel streams, ring 1): decided per stream by the entropy warp, uniform over the warp
+    const bool live = cons == 1 && lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
+    if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt, lc.publish);
+    else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
+        if (live) {
+            if (any8) stream_reg<8, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+            else stream_reg<6, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        } else if (any8) stream_reg<8, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        else stream_reg<6, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+    } else if (live) {
+        if (any8) stream_reg<8, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        else stream_reg<6, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+    } else if (any8) stream_reg<8, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+    else stream_reg<6, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+}
+
+// PREDICTOR warp, one group of 32 packets. The streams of a packet follow each other in the bitstream, so the entropy
+// warp produces them one at a time and one predictor warp serves both rings: ring 0 brings the mono / U stream of every
+// element (and the end of the group), its job says whether a V stream follows on ring 1 or whether ring 1 carries the
+// other half of an interleaved escape pair. `seq` lives across the groups of the CTA.
+__device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
                                                const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
                                                uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch,
                                                PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out,
-                                               uint64_t out_stride) {
-    const uint32_t pidx = blockIdx.x * 32u + lane;
+                                               uint64_t out_stride, uint32_t group, uint32_t *seq) {
+    const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
-    int32_t *scratch_lane = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u + lane;
-    uint32_t seq = 0;
+    int32_t *scratch_lane = scratch + lane;  // the CTA's own scratch, [slot][sample][lane]
     LiveCtx lc;
-    lc.u_base = scratch_lane - lane;  // slot 0 of the group: the U channel of a 2-channel stream
+    lc.u_base = scratch;  // slot 0: the U channel of a 2-channel stream
     lc.slot = pcm_out + (size_t)pidx * out_stride;
-    lc.desc = descs + pidx;
+    lc.desc = descs + lane;
     lc.frame_length = cfg.frame_length;
     lc.bps = cfg.bps;
     lc.bit_depth = cfg.bit_depth;
     lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
-    lc.enabled = cons == 1 && cfg.num_channels == 2u;
-    lc.publish = cons == 0 && cfg.num_channels == 2u;
-    RoleTimer rt(lane, 3 + 2 * cons);
+    lc.enabled = cfg.num_channels == 2u;
+    RoleTimer rt(lane, 3);
     const unsigned long long t_start = rt.now();
 #pragma unroll 1
     for (;;) {
-        const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        const uint32_t slot = seq[0] % RING_SLOTS, par = (seq[0] / RING_SLOTS) & 1u;
         const unsigned long long tw = rt.now();
-        mbar_wait(&sm.full_bar[cons][slot], par, 200);
+        mbar_wait(&sm.full_bar[0][slot], par, 200);
         rt.add(1, tw);
         Job jb;
-        jb.n = sm.job[cons][slot][0][lane];
-        const uint32_t meta = sm.job[cons][slot][1][lane];
-        jb.coef_bitpos = sm.job[cons][slot][2][lane];
-        jb.nmax = sm.job[cons][slot][3][lane];
-        jb.live = sm.job[cons][slot][4][lane];
-        jb.shift_bitpos = sm.job[cons][slot][5][lane];
-        jb.u_first_slot = sm.job[cons][slot][6][lane];
-        jb.kind = meta & 3u;
-        if (jb.kind == JOB_EXIT) {  // written for every lane
-            if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);  // pass it on to the emit warp
+        const uint32_t meta = read_job(sm, 0, slot, lane, jb);
+        if (jb.kind == JOB_EXIT) {  // written for every lane: the group is finished
+            mbar_arrive(&sm.empty_bar[0][slot]);
+            seq[0]++;
+            const uint32_t slot1 = seq[1] % RING_SLOTS, par1 = (seq[1] / RING_SLOTS) & 1u;
+            mbar_wait(&sm.full_bar[1][slot1], par1, 200);  // ring 1's end marker: pass it on to the emit warp
+            mbar_arrive(&sm.vdone_bar[slot1]);
+            mbar_arrive(&sm.empty_bar[1][slot1]);
+            seq[1]++;
             break;
         }
-        jb.order = (meta >> 2) & 31u;
-        jb.den = (meta >> 7) & 15u;
-        jb.mode = (meta >> 11) & 1u;
-        jb.chan_bits = (meta >> 12) & 63u;
-        jb.slot = (meta >> 18) & 7u;
-        jb.nmax = __shfl_sync(FULL_MASK, jb.nmax, 0);
         const bool active = valid && jb.kind != JOB_INACTIVE;
         int32_t *dst = scratch_lane + (size_t)jb.slot * cfg.frame_length * 32u;
-        const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
-        const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
-        const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
-        // live emission (2-channel streams, V warp): decided per stream by the entropy warp, uniform over the warp
-        const bool live = lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
-        if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt, lc.publish);
-        else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
-            if (live) {
-                if (any8) stream_reg<8, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-                else stream_reg<6, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-            } else if (any8) stream_reg<8, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-            else stream_reg<6, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        } else if (live) {
-            if (any8) stream_reg<8, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-            else stream_reg<6, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        } else if (any8) stream_reg<8, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        else stream_reg<6, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        lc.publish = cfg.num_channels == 2u;
+        if (meta & JOBF_PAIR) {
+            stream_escape_pair(sm, lane, seq, jb, active, dst, valid, cfg, scratch_lane, lc.publish, rt);
+            continue;
+        }
+        run_stream(sm, lane, 0, seq[0], pk, jb, active, dst, rt, lc);
+        if (meta & JOBF_V_FOLLOWS) {
+            const uint32_t slot1 = seq[1] % RING_SLOTS, par1 = (seq[1] / RING_SLOTS) & 1u;
+            const unsigned long long tw1 = rt.now();
+            mbar_wait(&sm.full_bar[1][slot1], par1, 200);
+            rt.add(1, tw1);
+            Job jv;
+            (void)read_job(sm, 1, slot1, lane, jv);
+            const bool active_v = valid && jv.kind != JOB_INACTIVE;
+            int32_t *dst_v = scratch_lane + (size_t)jv.slot * cfg.frame_length * 32u;
+            lc.publish = false;
+            run_stream(sm, lane, 1, seq[1], pk, jv, active_v, dst_v, rt, lc);
+        }
     }
     rt.add(0, t_start);
     rt.flush(3);
@@ -1564,8 +1729,8 @@ struct EmitArgs {
     const uint64_t *offsets;
     const uint32_t *sizes;
     uint32_t npackets;
-    const int32_t *scratch;
-    const PacketDesc *descs;
+    const int32_t *scratch;   // the CTA's own parked samples, [slot][sample][lane]
+    const PacketDesc *descs;  // the CTA's own 32 descriptors
     uint8_t *pcm_out;
     uint64_t out_stride;
 };
@@ -1663,7 +1828,7 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
     constexpr int EB = 16;           // frames per batch: 16*FB bytes = FB 128-bit stores
     constexpr uint32_t SROW = 21;    // shift words staged per lane and batch: 16 frames x 2 x 2 bytes + window + slack, odd
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    constexpr uint32_t NW = DEC_THREADS / 32;
+    constexpr uint32_t NW = DEC_WARPS;
     uint32_t *myrow = reinterpret_cast<uint32_t *>(smem) + ((size_t)warp * 32u + lane) * SROW;
     const uint32_t pidx = group * 32u + lane;
     const bool stereo = WIDTH == 2;
@@ -1671,7 +1836,7 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
     const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;
     const uint32_t sb = (merges_shift ? (uint32_t)op.shift : 0u) * 8u;
     const uint32_t n_op = min(op.n, n_final);  // output[:n] cuts what an earlier, longer element wrote
-    const int32_t *su = x.scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+    const int32_t *su = x.scratch + lane;
     const int32_t *sv = stereo ? su + (size_t)cfg.frame_length * 32u : su;
     uint8_t *slot = x.pcm_out + (size_t)pidx * x.out_stride;
     const bool vec_ok = ((((uintptr_t)x.pcm_out) | x.out_stride) & 15u) == 0;
@@ -1799,7 +1964,7 @@ __device__ __forceinline__ void emit_rows(const EmitArgs &x, const DevConfig &cf
     uint8_t *row = reinterpret_cast<uint8_t *>(roww);
     uint32_t *shrow = wbase + 32u * row_words + (size_t)lane * SHIFT_ROW;
     const uint32_t pidx = group * 32u + lane;
-    const int32_t *sbase = x.scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+    const int32_t *sbase = x.scratch + lane;
     uint8_t *slot = x.pcm_out + (size_t)pidx * x.out_stride;
     const bool depth20 = cfg.bit_depth == 20;
     const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;  // 16/20-bit writers ignore the shift buffer
@@ -1937,7 +2102,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
     uint32_t *shw = sw + 32u * row_words;                                             // this warp's shift rows
     const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < x.npackets;
-    const PacketDesc *desc = x.descs + pidx;
+    const PacketDesc *desc = x.descs + lane;
     int32_t st = ST_REF_PANIC;
     uint32_t nops = 0, n_final = 0;
     Packet pk{x.packed, 0};
@@ -2001,7 +2166,7 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
         }
     }
     uint8_t *row = reinterpret_cast<uint8_t *>(sw) + (size_t)lane * row_words * 4u;
-    const int32_t *sbase = x.scratch + (size_t)group * cfg.num_channels * cfg.frame_length * 32u + lane;
+    const int32_t *sbase = x.scratch + lane;
     const int bps = (int)cfg.bps;
     const bool depth20 = cfg.bit_depth == 20;
     const bool merges_shift = cfg.bit_depth == 24 || cfg.bit_depth == 32;  // 16/20-bit writers ignore the shift buffer
@@ -2127,18 +2292,22 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
     }
 }
 
-// decodePacketInto for 32 packets per CTA, decoder.go:133-207: role warps (stages 1+2), then the whole CTA emits.
-__global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8_t *__restrict__ packed,
-                                                                     const uint64_t *__restrict__ offsets,
-                                                                     const uint32_t *__restrict__ sizes, uint32_t npackets,
-                                                                     DevConfig cfg, int32_t *__restrict__ scratch,
-                                                                     PacketDesc *__restrict__ descs,
-                                                                     uint8_t *__restrict__ pcm_out, uint64_t out_stride,
-                                                                     uint32_t *__restrict__ out_bytes,
-                                                                     int32_t *__restrict__ status) {
+// decodePacketInto (decoder.go:133-207) for groups of 32 packets: persistent CTAs pull group after group from
+// counters[0]; per group the role warps run stages 1+2 (and stage 3 of live pairs), then the whole CTA emits what is left.
+// scratch / descs hold one slot per CTA (gridDim.x), not per group. counters = {next group, CTAs done}: both zero at
+// launch, and the last CTA to leave zeroes them again for the next launch on the same stream.
+__global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
+    const uint8_t *__restrict__ packed, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
+    uint32_t npackets, DevConfig cfg, int32_t *__restrict__ scratch, PacketDesc *__restrict__ descs,
+    uint8_t *__restrict__ pcm_out, uint64_t out_stride, uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status,
+    uint32_t *__restrict__ counters) {
     extern __shared__ __align__(1024) uint8_t dec_smem[];
     DecShared &sm = *reinterpret_cast<DecShared *>(dec_smem);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t ngroups = (npackets + 31u) / 32u;
+    uint32_t smid, hw_warp;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
     if (threadIdx.x == 0) {
         for (int c = 0; c < 2; c++)
             for (int s = 0; s < RING_SLOTS; s++) {
@@ -2147,62 +2316,72 @@ __global__ void __launch_bounds__(DEC_THREADS, 4) alac_decode_kernel(const uint8
             }
         for (int s = 0; s < RING_SLOTS; s++) mbar_init(&sm.vdone_bar[s], 32);
         sm.u_chunks_done = 0;
-        // The hardware puts the four warps of a CTA on the four SM sub-partitions (one each, starting anywhere), and the
-        // entropy warp is the one that must not share a scheduler with another entropy warp. Per SM, a packed word
-        // counts the resident entropy warps of every sub-partition; the CTA puts its own on the least loaded one.
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        sm.group = atomicAdd(&counters[0], 1u);
+    }
+    if (lane == 0) sm.warp_smsp[warp] = hw_warp & 3u;  // %warpid is a hint, but any assignment of roles is correct
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // The hardware spreads the warps of a CTA over the SM's sub-partitions, and the entropy warp is the one that must
+        // not share a scheduler with another entropy warp. Per SM, a packed word counts the resident entropy warps of
+        // every sub-partition; the CTA gives the role to its warp on the least loaded one, the predictor and emit roles
+        // to the following warps.
         unsigned int *word = &g_sm_entropy_load[smid & 255u];
-        const uint32_t first = atomicAdd(&g_sm_ticket[smid & 255u], 1u) & 3u;  // rotates the tie-break
+        const uint32_t first = atomicAdd(&g_sm_ticket[smid & 255u], 1u) % DEC_WARPS;  // rotates the tie-break
         unsigned int seen = *reinterpret_cast<volatile unsigned int *>(word), assumed;
         uint32_t best;
         do {
             assumed = seen;
             best = first;
-            for (uint32_t k = 1; k < 4; k++) {
-                const uint32_t sp = (first + k) & 3u;
-                if (((assumed >> (8 * sp)) & 0xffu) < ((assumed >> (8 * best)) & 0xffu)) best = sp;
+            for (uint32_t k = 1; k < DEC_WARPS; k++) {
+                const uint32_t w = (first + k) % DEC_WARPS;
+                if (((assumed >> (8 * sm.warp_smsp[w])) & 0xffu) < ((assumed >> (8 * sm.warp_smsp[best])) & 0xffu)) best = w;
             }
-            seen = atomicCAS(word, assumed, assumed + (1u << (8 * best)));
+            seen = atomicCAS(word, assumed, assumed + (1u << (8 * sm.warp_smsp[best])));
         } while (seen != assumed);
-        sm.rotation = best;
-        sm.subpart_mask = 0;
+        sm.entropy_smsp = sm.warp_smsp[best];
+        for (uint32_t k = 0; k < DEC_WARPS; k++) sm.role_of_warp[(best + k) % DEC_WARPS] = k;
     }
     __syncthreads();
-    // roles by sub-partition: entropy on the chosen one, then predictor 0, predictor 1, emit on the following ones.
-    // %warpid is only a hint: if the four warps do not report four different sub-partitions, roles go by warp index.
-    uint32_t hw_warp;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
-    if (lane == 0) atomicOr(&sm.subpart_mask, 1u << (hw_warp & 3u));
-    __syncthreads();
-    const uint32_t role = ((sm.subpart_mask == 0xfu ? hw_warp : warp) - sm.rotation) & 3u;
+    const uint32_t role = sm.role_of_warp[warp];
 #ifdef ALACB200_DEV
     if (g_role_cycles != nullptr && lane == 0) {  // developer aid: hardware warp slot of every warp of the CTA, by CTA warp index
-        uint32_t wid;
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        reinterpret_cast<volatile uint8_t *>(g_role_cycles + (size_t)blockIdx.x * 16 + 14)[warp] = (uint8_t)wid;
+        reinterpret_cast<volatile uint8_t *>(g_role_cycles + (size_t)blockIdx.x * 16 + 14)[warp] = (uint8_t)hw_warp;
         if (warp == 0) {
-            reinterpret_cast<volatile uint8_t *>(g_role_cycles + (size_t)blockIdx.x * 16 + 14)[4] = (uint8_t)(sm.rotation & 3u);
+            reinterpret_cast<volatile uint8_t *>(g_role_cycles + (size_t)blockIdx.x * 16 + 14)[4] = (uint8_t)(sm.entropy_smsp & 3u);
             g_role_cycles[(size_t)blockIdx.x * 16 + 15] = clock64();
         }
     }
 #endif
-    if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, out_bytes, status);
-    else if (role == 3) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
-    else predictor_warp(sm, lane, (int)role - 1, packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride);
-    __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
-    if (threadIdx.x == 0) {
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        atomicSub(&g_sm_entropy_load[smid & 255u], 1u << (8 * sm.rotation));
+    // the CTA's own slot of parked samples and element lists
+    int32_t *scratch_cta = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u;
+    PacketDesc *descs_cta = descs + (size_t)blockIdx.x * 32u;
+    uint32_t seq[2] = {0, 0};  // ring sequence numbers of this warp's role (the emit warp uses seq[1])
+    uint32_t u_seen = 0;       // emit warp: ring-0 slots known to be parked
+    uint32_t group = sm.group;
+#pragma unroll 1
+    while (group < ngroups) {
+        if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs_cta, out_bytes, status, group, seq, counters);
+        else if (role == 1) predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq);
+        else emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq[1], u_seen);
+        __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
+        // stage 3 of whatever was not emitted live reuses the window / ring / job memory as its transpose tiles
+        EmitArgs ea{packed, offsets, sizes, npackets, scratch_cta, descs_cta, pcm_out, out_stride};
+        RoleTimer rt(lane, 8 + (int)(warp % 3u));
+        const unsigned long long t_emit = rt.now();
+        emit_group<DEC_WARPS>(ea, cfg, group, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
+        rt.add(0, t_emit);
+        rt.flush(1);
+        group = sm.next_group;
+        __syncthreads();  // the tiles are free again; nobody reads next_group after this point
     }
-    // stage 3 reuses the window / ring / job memory as its transpose tile
-    EmitArgs ea{packed, offsets, sizes, npackets, scratch, descs, pcm_out, out_stride};
-    RoleTimer rt(lane, 8 + (int)(warp % 3u));
-    const unsigned long long t_emit = rt.now();
-    emit_group<DEC_THREADS / 32>(ea, cfg, blockIdx.x, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
-    rt.add(0, t_emit);
-    rt.flush(1);
+    if (threadIdx.x == 0) {
+        atomicSub(&g_sm_entropy_load[smid & 255u], 1u << (8 * sm.entropy_smsp));
+        __threadfence();
+        if (atomicAdd(&counters[1], 1u) == gridDim.x - 1u) {  // last CTA out: every fetch has been made
+            counters[0] = 0;
+            counters[1] = 0;
+        }
+    }
 }
 
 }  // namespace alacb200

@@ -136,6 +136,47 @@ func statusError(status int32) error {
 // ErrMalformedPacket is returned where the reference implementation would panic on a hostile packet.
 var ErrMalformedPacket = fmt.Errorf("alac: malformed packet")
 
+// ErrCUDA wraps failures of the device or of pinned-memory allocation (there is no CPU fallback).
+var ErrCUDA = fmt.Errorf("alac: cuda")
+
+// arena returns the decoder-owned pinned staging buffers (grow-only, alacb200_arena): packets are packed into `in`,
+// PCM comes back through `out`. A steady stream of DecodePacket / DecodePackets calls allocates no pinned memory,
+// like the reference decoder keeps its scratch (decoder.go:79-87).
+func (d *PacketDecoder) arena(inBytes, outBytes int) (in, out []byte, err error) {
+	var inPtr, outPtr *C.uint8_t
+
+	if rc := C.alacb200_arena(d.h, C.uint64_t(inBytes), C.uint64_t(outBytes), &inPtr, &outPtr); rc != C.ALACB200_OK {
+		return nil, nil, fmt.Errorf("%w: %w: %s", ErrDecode, ErrCUDA, C.GoString(C.alacb200_last_error()))
+	}
+
+	if inPtr == nil || outPtr == nil {
+		return nil, nil, fmt.Errorf("%w: %w: pinned arena unavailable", ErrDecode, ErrCUDA)
+	}
+
+	return unsafe.Slice((*byte)(unsafe.Pointer(inPtr)), max(inBytes, 1)), unsafe.Slice((*byte)(unsafe.Pointer(outPtr)), max(outBytes, 1)), nil
+}
+
+// decodeInPlace decodes the packets data[offsets[i] : offsets[i]+sizes[i]] (data: the pinned arena or any other
+// host bytes, e.g. a whole file image with its sample table) into the arena's output half.
+// status[i] == ALACB200_ST_IO_TRUNCATED marks a packet that lies outside data: a READ error, not a decode error.
+func (d *PacketDecoder) decodeInPlace(data []byte, offsets []C.uint64_t, sizes []C.uint32_t, out []byte, stride int,
+) (outBytes []C.uint32_t, status []C.int32_t, err error) {
+	count := len(sizes)
+	outBytes = make([]C.uint32_t, count)
+	status = make([]C.int32_t, count)
+
+	rc := C.alacb200_decode_packets(d.h, (*C.uint8_t)(unsafe.Pointer(unsafe.SliceData(data))), C.uint64_t(len(data)),
+		&offsets[0], &sizes[0], C.uint32_t(count), (*C.uint8_t)(unsafe.Pointer(unsafe.SliceData(out))), C.uint64_t(stride),
+		&outBytes[0], &status[0])
+	if rc != C.ALACB200_OK {
+		return nil, nil, fmt.Errorf("%w: %w: %s", ErrDecode, ErrCUDA, C.GoString(C.alacb200_last_error()))
+	}
+
+	return outBytes, status, nil
+}
+
+func (d *PacketDecoder) stride() int { return (int(C.alacb200_max_packet_pcm_bytes(d.h)) + 3) &^ 3 }
+
 // DecodePackets decodes many packets in one GPU call. pcm[i] is a fresh slice of numSamples*channels*bps bytes
 // (shorter for a partial last packet) or nil with errs[i] set, i.e. exactly what n calls of DecodePacket return.
 func (d *PacketDecoder) DecodePackets(packets [][]byte) ([][]byte, []error) {
@@ -147,7 +188,15 @@ func (d *PacketDecoder) DecodePackets(packets [][]byte) ([][]byte, []error) {
 		return pcm, errs
 	}
 
-	// Host packer: one pinned buffer, every packet on a 16-byte boundary.
+	fail := func(err error) ([][]byte, []error) {
+		for idx := range errs {
+			errs[idx] = err
+		}
+
+		return pcm, errs
+	}
+
+	// Host packer: the decoder's pinned arena, every packet on a 16-byte boundary.
 	offsets := make([]C.uint64_t, count)
 	sizes := make([]C.uint32_t, count)
 	total := 0
@@ -158,33 +207,21 @@ func (d *PacketDecoder) DecodePackets(packets [][]byte) ([][]byte, []error) {
 		total += (len(packet) + 15) &^ 15
 	}
 
-	stride := (int(C.alacb200_max_packet_pcm_bytes(d.h)) + 3) &^ 3
-	packedPtr := C.alacb200_pinned_alloc(C.size_t(total + 64))
-	pcmPtr := C.alacb200_pinned_alloc(C.size_t(count * stride))
+	stride := d.stride()
 
-	defer C.alacb200_pinned_free(packedPtr)
-	defer C.alacb200_pinned_free(pcmPtr)
+	in, out, err := d.arena(total, count*stride)
+	if err != nil {
+		return fail(err)
+	}
 
-	packed := unsafe.Slice((*byte)(packedPtr), total+64)
 	for idx, packet := range packets {
-		copy(packed[int(offsets[idx]):], packet)
+		copy(in[int(offsets[idx]):], packet)
 	}
 
-	outBytes := make([]C.uint32_t, count)
-	status := make([]C.int32_t, count)
-
-	rc := C.alacb200_decode_packets(d.h, (*C.uint8_t)(packedPtr), &offsets[0], &sizes[0], C.uint32_t(count),
-		(*C.uint8_t)(pcmPtr), C.uint64_t(stride), &outBytes[0], &status[0])
-	if rc != C.ALACB200_OK {
-		err := fmt.Errorf("%w: cuda: %s", ErrDecode, C.GoString(C.alacb200_last_error()))
-		for idx := range errs {
-			errs[idx] = err
-		}
-
-		return pcm, errs
+	outBytes, status, err := d.decodeInPlace(in[:total], offsets, sizes, out, stride)
+	if err != nil {
+		return fail(err)
 	}
-
-	out := unsafe.Slice((*byte)(pcmPtr), count*stride)
 
 	for idx := range packets {
 		if status[idx] != C.ALACB200_ST_OK {
@@ -205,3 +242,8 @@ func (d *PacketDecoder) DecodePacket(packet []byte) ([]byte, error) {
 
 	return pcm[0], errs[0]
 }
+
+// sentinels of internal/alac/errors.go:24-33 used by library_cgo.go
+func alacintErrInvalidCookie() error      { return alacint.ErrInvalidCookie }
+func alacintErrUnsupportedVersion() error { return alacint.ErrUnsupportedVersion }
+func alacintErrBitDepth() error           { return alacint.ErrBitDepth }

@@ -6,6 +6,7 @@
 //   alac::ParseMagicCookie            config.go:47-81
 //   alac::PacketDecoder               decoder.go:79-128   (NewPacketDecoder, DecodePacket, Format)
 //   alac::PacketDecoder::DecodePackets  NEW: the batched entry point of the north star
+//   alac::LibraryDecoder              NEW: many tracks of mixed cookies in one call, sharded over devices
 //   alac::Decoder                     decode.go:32-190    (NewDecoder, Read, Seek, Duration, Position, Format)
 //   alac::Error{Config,NoTrack,Decode}  errors.go:22-34, message = the reference's %w chain
 //
@@ -31,7 +32,7 @@ struct PCMFormat {  // format.go:20-24
     int SampleRate, BitDepth, Channels;
 };
 
-enum class ErrKind { Config, NoTrack, Decode, Device };  // ErrConfig / ErrNoTrack / ErrDecode (+ CUDA unusable)
+enum class ErrKind { Config, NoTrack, Decode, Device, Read };  // ErrConfig / ErrNoTrack / ErrDecode (+ CUDA unusable, reader failure)
 
 class Error : public std::runtime_error {
 public:
@@ -84,35 +85,48 @@ public:
     PCMFormat Format() const { return PCMFormat{(int)cfg_.sample_rate, cfg_.bit_depth, cfg_.num_channels}; }  // decoder.go:112
     const PacketConfig &Config() const { return cfg_; }
 
-    // DecodePackets: one batched GPU call for many packets (possibly of several tracks with this cookie).
+    // DecodePackets: one batched GPU call for many packets (possibly of several tracks with this cookie). The packets
+    // are packed into the decoder's own pinned arena and the PCM comes back through it: no pinned allocation per call.
     std::vector<PacketResult> DecodePackets(const std::vector<std::pair<const uint8_t *, size_t>> &packets) {
         const uint32_t n = (uint32_t)packets.size();
         std::vector<PacketResult> out(n);
         if (n == 0) return out;
-        // host packer: contiguous buffer, every packet on a 16-byte boundary
         std::vector<uint64_t> offsets(n);
         std::vector<uint32_t> sizes(n);
         uint64_t pos = 0;
-        for (uint32_t i = 0; i < n; i++) {
+        for (uint32_t i = 0; i < n; i++) {  // host packer: every packet on a 16-byte boundary
             offsets[i] = pos;
             sizes[i] = (uint32_t)packets[i].second;
             pos += (packets[i].second + 15) / 16 * 16;
         }
-        std::vector<uint8_t> packed(pos + 64, 0);
+        const uint64_t stride = Stride();
+        uint8_t *in = nullptr, *pcm = nullptr;
+        if (alacb200_arena(h_, pos, (uint64_t)n * stride, &in, &pcm) != ALACB200_OK)
+            throw Error(ErrKind::Device, 0, std::string("alacb200_arena: ") + alacb200_last_error());
         for (uint32_t i = 0; i < n; i++)
-            if (sizes[i]) std::memcpy(packed.data() + offsets[i], packets[i].first, sizes[i]);
-        const uint64_t stride = (alacb200_max_packet_pcm_bytes(h_) + 3) / 4 * 4;
-        std::vector<uint8_t> pcm((size_t)n * stride);
+            if (sizes[i]) std::memcpy(in + offsets[i], packets[i].first, sizes[i]);
         std::vector<uint32_t> nbytes(n);
         std::vector<int32_t> status(n);
-        const int32_t rc = alacb200_decode_packets(h_, packed.data(), offsets.data(), sizes.data(), n, pcm.data(), stride,
-                                                   nbytes.data(), status.data());
-        if (rc != ALACB200_OK) throw Error(ErrKind::Device, 0, std::string("alacb200_decode_packets: ") + alacb200_last_error());
+        DecodeInPlace(in, pos, offsets.data(), sizes.data(), n, pcm, nbytes.data(), status.data());
         for (uint32_t i = 0; i < n; i++) {
-            if (status[i] == ALACB200_ST_OK) out[i].pcm.assign(pcm.begin() + (size_t)i * stride, pcm.begin() + (size_t)i * stride + nbytes[i]);
+            if (status[i] == ALACB200_ST_OK) out[i].pcm.assign(pcm + (size_t)i * stride, pcm + (size_t)i * stride + nbytes[i]);
             else out[i].err.reset(new Error(error_from_status(status[i])));
         }
         return out;
+    }
+
+    // Packets read in place from `data` (a file image with its sample table, or packed packets): PCM rows of Stride()
+    // bytes into pcm. status ALACB200_ST_IO_TRUNCATED marks a packet outside data (a READ error, decode.go:172-174).
+    void DecodeInPlace(const uint8_t *data, uint64_t data_len, const uint64_t *offsets, const uint32_t *sizes, uint32_t n, uint8_t *pcm,
+                       uint32_t *nbytes, int32_t *status) {
+        const int32_t rc = alacb200_decode_packets(h_, data, data_len, offsets, sizes, n, pcm, Stride(), nbytes, status);
+        if (rc != ALACB200_OK) throw Error(ErrKind::Device, 0, std::string("alacb200_decode_packets: ") + alacb200_last_error());
+    }
+    uint64_t Stride() const { return (alacb200_max_packet_pcm_bytes(h_) + 3) / 4 * 4; }
+    // the decoder's pinned arena (grow-only, valid until the next Arena / DecodePackets call)
+    void Arena(uint64_t in_bytes, uint64_t out_bytes, uint8_t **in, uint8_t **out) {
+        if (alacb200_arena(h_, in_bytes, out_bytes, in, out) != ALACB200_OK)
+            throw Error(ErrKind::Device, 0, std::string("alacb200_arena: ") + alacb200_last_error());
     }
 
     // DecodePacket, decoder.go:117-128: a fresh buffer of numSamples*channels*bps bytes, or the error.
@@ -135,7 +149,7 @@ class Decoder {
 public:
     using Duration_ns = int64_t;
 
-    static std::unique_ptr<Decoder> New(std::vector<uint8_t> file, int device = 0, size_t window = 2048) {  // NewDecoder, decode.go:50-75
+    static std::unique_ptr<Decoder> New(const std::vector<uint8_t> &file, int device = 0, size_t window = 2048) {  // NewDecoder, decode.go:50-75
         alacb200_track *t = nullptr;
         const int32_t rc = alacb200_mp4_find_alac_track(file.data(), file.size(), &t);
         std::unique_ptr<alacb200_track, void (*)(alacb200_track *)> guard(t, alacb200_mp4_free_track);
@@ -151,12 +165,29 @@ public:
         uint64_t ns = 0;
         const alacb200_sample_info *si = alacb200_mp4_samples(t, &ns);
         std::unique_ptr<Decoder> d(new Decoder());
-        d->file_ = std::move(file);
         d->samples_.assign(si, si + ns);
+        d->offsets_.resize(ns);
+        d->sizes_.resize(ns);
+        for (uint64_t k = 0; k < ns; k++) {
+            d->offsets_[k] = si[k].offset;
+            d->sizes_[k] = si[k].size;
+        }
         d->dec_ = PacketDecoder::New(cfg, device);
         d->window_ = std::max<size_t>(1, window);
+        // the file image lives in pinned memory for the life of the decoder: every window is read in place from it
+        // (image + sample table straight to the C ABI, asynchronous H2D), nothing is re-packed
+        d->image_len_ = file.size();
+        d->image_ = (uint8_t *)alacb200_pinned_alloc(std::max<size_t>(1, file.size()));
+        if (!d->image_) throw Error(ErrKind::Device, 0, std::string("alacb200_pinned_alloc: ") + alacb200_last_error());
+        std::memcpy(d->image_, file.data(), file.size());
         return d;
     }
+    ~Decoder() {
+        dec_.reset();
+        alacb200_pinned_free(image_);
+    }
+    Decoder(const Decoder &) = delete;
+    Decoder &operator=(const Decoder &) = delete;
 
     PCMFormat Format() const { return dec_->Format(); }
     Duration_ns Duration() const {  // decode.go:82-88
@@ -169,7 +200,9 @@ public:
     }
     Duration_ns Seek(Duration_ns t) {  // decode.go:103-124
         const auto &c = dec_->Config();
-        const int64_t frame = (int64_t)(((double)t / 1e9) * (double)c.sample_rate);
+        // time.Duration.Seconds(): whole seconds plus the nanosecond rest, each converted on its own
+        const double seconds = (double)(t / 1000000000ll) + (double)(t % 1000000000ll) / 1e9;
+        const int64_t frame = (int64_t)(seconds * (double)c.sample_rate);
         int64_t target = frame / (int64_t)c.frame_length;
         target = std::max<int64_t>(0, std::min<int64_t>(target, (int64_t)samples_.size()));
         sample_idx_ = (size_t)target;
@@ -209,40 +242,124 @@ private:
     Decoder() = default;
     void fill() {
         const size_t idx = sample_idx_;
-        if (!(idx >= ready_base_ && idx < ready_base_ + ready_.size())) {
+        if (!(idx >= ready_base_ && idx < ready_base_ + ready_n_)) {
             const size_t hi = std::min(samples_.size(), idx + window_);
-            std::vector<std::pair<const uint8_t *, size_t>> pk;
-            bool short_read = false;
-            for (size_t k = idx; k < hi; k++) {
-                const auto &s = samples_[k];
-                if (s.offset > file_.size() || s.size > file_.size() - s.offset) {  // io.ReadFull fails, decode.go:172-174
-                    short_read = true;
-                    break;
-                }
-                pk.emplace_back(file_.data() + s.offset, s.size);
-            }
-            ready_ = dec_->DecodePackets(pk);
-            if (short_read) {
-                PacketResult r;
-                r.err.reset(new Error(ErrKind::Decode, 0, "reading sample " + std::to_string(idx + pk.size()) + ": unexpected EOF"));
-                ready_.push_back(std::move(r));
-            }
+            const uint32_t n = (uint32_t)(hi - idx);
+            const uint64_t stride = dec_->Stride();
+            uint8_t *in = nullptr, *pcm = nullptr;
+            dec_->Arena(0, (uint64_t)n * stride, &in, &pcm);
+            ready_nbytes_.assign(n, 0);
+            ready_status_.assign(n, 0);
+            dec_->DecodeInPlace(image_, image_len_, offsets_.data() + idx, sizes_.data() + idx, n, pcm, ready_nbytes_.data(), ready_status_.data());
+            ready_pcm_ = pcm;  // the arena is only reused by this decoder's next window
+            ready_stride_ = stride;
             ready_base_ = idx;
+            ready_n_ = n;
         }
-        PacketResult &r = ready_[idx - ready_base_];
-        if (r.err) throw Error(r.err->kind, r.err->status, "decoding packet " + std::to_string(idx) + ": " + r.err->what());  // decode.go:181
-        buf_ = r.pcm;
+        const size_t k = idx - ready_base_;
+        const int32_t st = ready_status_[k];
+        if (ALACB200_ST_CODE(st) == ALACB200_ST_IO_TRUNCATED)  // io.ReadFull fails, decode.go:172-174: not a decode error
+            throw Error(ErrKind::Read, st, "reading sample " + std::to_string(idx) + ": unexpected EOF");
+        if (st != ALACB200_ST_OK) {
+            const Error e = error_from_status(st);
+            throw Error(e.kind, e.status, "decoding packet " + std::to_string(idx) + ": " + e.what());  // decode.go:181
+        }
+        buf_.assign(ready_pcm_ + k * ready_stride_, ready_pcm_ + k * ready_stride_ + ready_nbytes_[k]);
         buf_off_ = 0;
         sample_idx_++;
     }
 
-    std::vector<uint8_t> file_;
+    uint8_t *image_ = nullptr;  // pinned copy of the file
+    size_t image_len_ = 0;
     std::vector<alacb200_sample_info> samples_;
+    std::vector<uint64_t> offsets_;
+    std::vector<uint32_t> sizes_;
     std::unique_ptr<PacketDecoder> dec_;
-    size_t sample_idx_ = 0, window_ = 2048, ready_base_ = 0, buf_off_ = 0;
-    std::vector<PacketResult> ready_;
+    size_t sample_idx_ = 0, window_ = 2048, ready_base_ = 0, ready_n_ = 0, buf_off_ = 0;
+    const uint8_t *ready_pcm_ = nullptr;
+    uint64_t ready_stride_ = 0;
+    std::vector<uint32_t> ready_nbytes_;
+    std::vector<int32_t> ready_status_;
     std::vector<uint8_t> buf_;
     bool eof_ = false;
+};
+
+// Many tracks of mixed cookies in one call, sharded over the devices of the box (BASELINE configs[4]). A
+// PacketDecoder holds one cookie (decoder.go:79-87); the library handle checks every track like ParseMagicCookie +
+// NewPacketDecoder, balances contiguous track ranges over the devices by compressed bytes and reads every track's
+// packets in place.
+struct TrackInput {
+    const uint8_t *cookie;
+    size_t cookie_len;
+    const uint8_t *data;  // file image or packed packets (pin it for asynchronous copies)
+    uint64_t data_len;
+    const uint64_t *offsets;
+    const uint32_t *sizes;
+    uint32_t n;
+};
+struct TrackOutput {
+    PacketConfig config{};
+    std::unique_ptr<Error> err;  // ErrConfig: the track has no decoder
+    uint64_t stride = 0;
+    std::vector<uint8_t> pcm;    // n rows of `stride` bytes; packet i is the first out_bytes[i] of row i
+    std::vector<uint32_t> out_bytes;
+    std::vector<int32_t> status;
+    int device = -1;
+};
+class LibraryDecoder {
+public:
+    static std::unique_ptr<LibraryDecoder> New(const std::vector<int> &devices = {0}) {
+        alacb200_library *h = nullptr;
+        if (alacb200_library_create(devices.data(), (int)devices.size(), &h) != ALACB200_OK)
+            throw Error(ErrKind::Device, 0, std::string("alacb200_library_create: ") + alacb200_last_error());
+        return std::unique_ptr<LibraryDecoder>(new LibraryDecoder(h));
+    }
+    ~LibraryDecoder() { alacb200_library_destroy(h_); }
+    LibraryDecoder(const LibraryDecoder &) = delete;
+    LibraryDecoder &operator=(const LibraryDecoder &) = delete;
+
+    std::vector<TrackOutput> DecodeTracks(const std::vector<TrackInput> &tracks) {
+        const uint32_t nt = (uint32_t)tracks.size();
+        std::vector<TrackOutput> out(nt);
+        std::vector<alacb200_track_desc> descs(nt);
+        for (uint32_t t = 0; t < nt; t++) {
+            const TrackInput &in = tracks[t];
+            alacb200_track_desc &d = descs[t];
+            std::memset(&d, 0, sizeof d);
+            PacketConfig cfg;
+            uint64_t stride = 4;
+            if (alacb200_parse_cookie(in.cookie, in.cookie_len, &cfg) == ALACB200_ST_OK && alacb200_bytes_per_sample(cfg.bit_depth) > 0)
+                stride = ((uint64_t)cfg.frame_length * cfg.num_channels * alacb200_bytes_per_sample(cfg.bit_depth) + 3) / 4 * 4;
+            out[t].stride = stride;
+            out[t].pcm.assign((size_t)in.n * stride + 1, 0);
+            out[t].out_bytes.assign(in.n + 1, 0);
+            out[t].status.assign(in.n + 1, 0);
+            d.cookie = in.cookie; d.cookie_len = in.cookie_len;
+            d.data = in.data; d.data_len = in.data_len;
+            d.offsets = in.offsets; d.sizes = in.sizes; d.n = in.n;
+            d.pcm_out = out[t].pcm.data(); d.out_stride = stride;
+            d.out_bytes = out[t].out_bytes.data(); d.status = out[t].status.data();
+        }
+        if (alacb200_library_decode_tracks(h_, descs.data(), nt) != ALACB200_OK)
+            throw Error(ErrKind::Device, 0, std::string("alacb200_library_decode_tracks: ") + alacb200_last_error());
+        for (uint32_t t = 0; t < nt; t++) {
+            out[t].config = descs[t].config;
+            out[t].device = descs[t].device;
+            if (descs[t].result == ALACB200_E_CONFIG) {
+                Error e = error_from_status(descs[t].track_status);
+                if (descs[t].track_status == ALACB200_ST_BIT_DEPTH)
+                    e = Error(e.kind, e.status, std::string(e.what()) + ": " + std::to_string(descs[t].config.bit_depth));  // decoder.go:92
+                out[t].err.reset(new Error(e));
+            } else if (descs[t].result != ALACB200_OK) {
+                out[t].err.reset(new Error(ErrKind::Device, 0, "track " + std::to_string(t) + ": rc=" + std::to_string(descs[t].result)));
+            }
+        }
+        return out;
+    }
+
+private:
+    explicit LibraryDecoder(alacb200_library *h) : h_(h) {}
+    alacb200_library *h_;
 };
 
 }  // namespace alac
