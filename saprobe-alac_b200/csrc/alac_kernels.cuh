@@ -212,27 +212,37 @@ struct RoleTimer {
 #endif
 
 // ---- geometry of one decode CTA ---------------------------------------------------------------------
-// 3 warps work on one group of 32 packets at a time (lane = packet); a CTA is persistent and pulls group after group
-// from a counter. The ENTROPY warp hands residual codes, 32 samples at a time, through two shared-memory rings to the
-// PREDICTOR warp: ring 0 carries the mono / U stream of every element, ring 1 the V stream (the streams of a packet
-// follow each other in the bitstream, so one predictor warp serves both rings in turn); the EMIT warp follows ring 1.
+// A CTA works on one group of 32 packets at a time (lane = packet); it is persistent and pulls group after group from a
+// counter. The ENTROPY warp hands residual codes, 32 samples at a time, through two shared-memory rings to the PREDICTOR
+// warp: ring 0 carries the mono / U stream of every element, ring 1 the V stream (the streams of a packet follow each
+// other in the bitstream, so one predictor warp serves both rings in turn); the EMIT warp follows ring 1. The fourth
+// warp only joins for the tail. It is there for the hardware's sake: the four warps of a CTA land on the four SM
+// sub-partitions, so every CTA can put its entropy warp on the least loaded scheduler; with three-warp CTAs (five per
+// SM) the warp slots came out uneven over the sub-partitions (one of them got 32 % of the warps) and everything was
+// 9-13 % slower (profiles/r02a).
+#if defined(ALACB200_THREE_WARPS)  // experiment
 constexpr int DEC_THREADS = 96;
+constexpr int CTAS_PER_SM = 5;
+#else
+constexpr int DEC_THREADS = 128;
+constexpr int CTAS_PER_SM = 4;   // 128 threads x 128 registers; ~38 KB of shared memory per CTA
+#endif
 constexpr int DEC_WARPS = DEC_THREADS / 32;
-constexpr int CTAS_PER_SM = 5;   // 96 threads x 128 registers and ~42 KB of shared memory per CTA
 constexpr int RING_SLOTS = 2;    // ring depth per consumer
 constexpr int CHUNK = 32;        // samples per ring slot
-constexpr int FIFO_CHUNKS = 32;  // 16-byte chunks of compressed bytes staged per lane (512 B window)
+constexpr int FIFO_CHUNKS = 16;  // 16-byte chunks of compressed bytes staged per lane (256 B window)
 constexpr int LIVE_SHIFT_CHUNKS = 10;  // 16-byte chunks covering 32 frames x 2 channels x 2 shift bytes at any alignment
 
 struct DecShared {
-    // Compressed bytes staged by cp.async: a 512-byte window per lane, [lane][chunk ^ (lane & 7)]. The window of a lane
-    // starts on a 512-byte boundary of the shared address space (the struct sits at a 1024-byte aligned base), so the
-    // address of a word is one LOP3: (byte offset & 0x1fc) ^ window base; the XOR spreads the lanes over the banks.
+    // Compressed bytes staged by cp.async: a 256-byte window per lane, [lane][chunk ^ (lane & 7)]. The window of a lane
+    // starts on a 256-byte boundary of the shared address space (the struct sits at a 1024-byte aligned base), so the
+    // address of a word is one LOP3: (byte offset & 0xfc) ^ window base; the XOR spreads the lanes over the banks.
     uint4 fifo[32][FIFO_CHUNKS];
     int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (16 KB)
     uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
                                              // live-emit word, shift bit position, first consumer-0 slot of the U stream
-    // live emission (2-channel streams): the shift bytes of the current 32-frame chunk
+    // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
+    int32_t live_u[CHUNK][32];
     uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
     // barriers last: stage 3 reuses everything in front of them as its transpose tiles
     uint64_t full_bar[2][RING_SLOTS];
@@ -245,7 +255,7 @@ struct DecShared {
     uint32_t warp_smsp[DEC_WARPS];      // sub-partition every warp reports
     uint32_t role_of_warp[DEC_WARPS];
 };
-static_assert(offsetof(DecShared, fifo) == 0 && FIFO_CHUNKS * 16 == 512, "lane windows must be 512-byte aligned");
+static_assert(offsetof(DecShared, fifo) == 0 && (FIFO_CHUNKS & (FIFO_CHUNKS - 1)) == 0 && FIFO_CHUNKS >= 16, "lane windows must be aligned to their size");
 static_assert(offsetof(DecShared, ring) % 16 == 0 && offsetof(DecShared, live_shift) % 16 == 0 && offsetof(DecShared, full_bar) % 8 == 0, "alignment");
 
 
@@ -283,6 +293,7 @@ struct BitReader {
     uint32_t end_rel;      // packet end, bytes from gbase
     uint32_t fifo;         // shared address of this lane's window, XORed with the lane's bank swizzle
     uint32_t req;          // next 16-byte chunk to request
+    uint32_t landed;       // chunks below this one have landed (requested before the last wait)
     uint32_t qo;           // byte offset from gbase (multiple of 4) of the next word to load; hi, lo are the two before it
     uint32_t hi, lo;       // big-endian-converted words
     uint32_t sh;           // bits of hi already consumed (0..31)
@@ -302,11 +313,18 @@ struct BitReader {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
         return __byte_perm(v, 0, 0x0123);
     }
-    // land what was requested a period ago, request up to a full window ahead of the reader
+    // land what was requested a period ago, request up to a full window ahead of the reader. 16 samples eat at most
+    // 16 x 67 bits = 134 bytes (+ the two words in hand): if a run of maximal codes has brought the reader that close to
+    // what had landed, wait for the new requests as well (never the case on real streams).
     __device__ __forceinline__ void top_up() {
         wait_all();
+        landed = req;
         const uint32_t lim = (qo >> 4) + FIFO_CHUNKS;
         while (req < lim) request(req++);
+        if (qo + 160u > (landed << 4)) {
+            wait_all();
+            landed = req;
+        }
     }
     __device__ __forceinline__ void init(const Packet &pk, uint32_t bp, uint32_t fifo_addr) {
         const uintptr_t a = (uintptr_t)pk.p;
@@ -322,6 +340,7 @@ struct BitReader {
         const uint32_t lim = req + FIFO_CHUNKS;
         while (req < lim) request(req++);
         wait_all();
+        landed = req;
         hi = load(q);
         lo = load(q + 4u);
         qo = q + 8u;
@@ -1022,11 +1041,23 @@ struct LiveCtx {
     bool publish;  // U / mono predictor warp of a 2-channel stream: the emit warp reads its parked samples back
 };
 
-// Start fetching what the emission of chunk `ck` needs besides the samples: this lane's shift bytes, by cp.async so they
-// land while the predictor runs.
-__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const Packet &pk, uint32_t ck, bool live_lane,
-                                              uint32_t n_lane, uint32_t sb, uint32_t shift_bitpos, uint32_t &rel0) {
+// Start fetching what the emission of chunk `ck` needs: the parked U samples of the 32 frames (one 4 KB block,
+// cooperative) and this lane's shift bytes, all by cp.async so they land while the predictor runs.
+__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const LiveCtx &lc, const Packet &pk, uint32_t ck,
+                                              bool live_lane, uint32_t n_lane, uint32_t sb, uint32_t shift_bitpos,
+                                              uint32_t &rel0) {
     const uint32_t base_i = ck * CHUNK;
+    const uint8_t *ug = reinterpret_cast<const uint8_t *>(lc.u_base + (size_t)base_i * 32u);
+    const uint32_t frames_left = lc.frame_length > base_i ? lc.frame_length - base_i : 0u;
+    const uint32_t ubase = smem_u32(&sm.live_u[0][0]);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const uint32_t piece = k * 32u + lane;                  // 16-byte piece of the 4 KB block: frame = piece / 8
+        const uint32_t nb = (piece >> 3) < frames_left ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ubase + piece * 16u),
+                     "l"(ug + (nb ? (size_t)piece * 16u : 0)), "r"(nb)
+                     : "memory");
+    }
     rel0 = 0;
     const uint32_t cnt = (live_lane && n_lane > base_i) ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
     if (sb && cnt) {
@@ -1052,9 +1083,9 @@ __device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, cons
     }
 }
 
-// Generic (any depth / shift) emission of the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from the
-// parked samples (loaded here: this is the cold path), shift bytes from live_shift; two batches of 16 frames, each
-// leaving as 2*BPS 128-bit stores to the lane's own packet slot (matrix.go:30-215).
+// Generic (any depth / shift) emission of the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u,
+// shift bytes from live_shift; two batches of 16 frames, each leaving as 2*BPS 128-bit stores to the lane's own packet
+// slot (matrix.go:30-215).
 template <int BPS>
 __device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
@@ -1070,16 +1101,13 @@ __device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, con
         const uint32_t f0 = ck * CHUNK + half * EB;
         if (f0 >= lc.frame_length) break;
         const uint32_t cnt = n_lane > f0 ? min((uint32_t)EB, n_lane - f0) : 0u;
-        int32_t uv[EB];
-#pragma unroll
-        for (int q = 0; q < EB; q++) uv[q] = f0 + (uint32_t)q < lc.frame_length ? __ldcg(lc.u_base + (size_t)(f0 + q) * 32u + lane) : 0;
         uint32_t ow[4 * FB];
 #pragma unroll
         for (int k = 0; k < 4 * FB; k++) ow[k] = 0;
 #pragma unroll
         for (int q = 0; q < EB; q++) {
             const uint32_t jq = half * EB + (uint32_t)q;
-            int32_t left = uv[q], right = vsrc[jq * 32u];
+            int32_t left = sm.live_u[jq][lane], right = vsrc[jq * 32u];
             if (mix_res != 0) {  // matrix.go:40-41
                 const int32_t v = right;
                 left = left + v - sar_go(mix_res * v, mix_bits);
@@ -1153,14 +1181,14 @@ __device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint
     }
 }
 
-// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from registers (uv), shift bytes from live_shift;
-// two batches of 16 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
+// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u, shift bytes from live_shift; two
+// batches of 16 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
 // The two shapes real streams have -- 16-bit, and 24-bit with one shifted byte -- are packed with byte permutes
 // (3 PRMT per 2 frames); everything else takes the generic path.
 template <int BPS>
 __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
-                                          const int32_t *vsrc, const int32_t (&uv)[CHUNK]) {
+                                          const int32_t *vsrc) {
     const bool fast = (BPS == 2 && lc.bit_depth == 16) || (BPS == 3 && lc.bit_depth == 24 && sb == 8u);
     if (!__all_sync(FULL_MASK, fast)) {
         live_emit_generic<BPS>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
@@ -1169,8 +1197,8 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
     const int32_t mix_res = (int32_t)(int8_t)((live_word >> 8) & 0xffu);
     const uint32_t mix_bits = live_word & 0xffu;
     const uint32_t *shrow = reinterpret_cast<const uint32_t *>(&sm.live_shift[lane][0]);
-#pragma unroll
-    for (int half = 0; half < 2; half++) {  // unrolled: uv is indexed statically
+#pragma unroll 1
+    for (uint32_t half = 0; half < 2; half++) {
         const uint32_t f0 = ck * CHUNK + half * 16u;
         if (f0 >= lc.frame_length) break;
         const uint32_t cnt = n_lane > f0 ? min(16u, n_lane - f0) : 0u;
@@ -1190,9 +1218,9 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int q = 2 * pr + e;
-                    const int jq = half * 16 + q;
+                    const uint32_t jq = half * 16u + (uint32_t)q;
                     int32_t left, right;
-                    unmix(uv[jq], vsrc[jq * 32], mix_res, mix_bits, left, right);
+                    unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
                     // (x << 8) | shift byte (matrix.go:132-135): frame 2k sits in the upper half of S[k], 2k+1 in the lower
                     uint32_t l24 = __byte_perm(S[pr], (uint32_t)left, e == 0 ? 0x6543 : 0x6541);
                     uint32_t r24 = __byte_perm(S[pr], (uint32_t)right, e == 0 ? 0x6542 : 0x6540);
@@ -1209,9 +1237,9 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
             uint32_t ow[16];
 #pragma unroll
             for (int q = 0; q < 16; q++) {
-                const int jq = half * 16 + q;
+                const uint32_t jq = half * 16u + (uint32_t)q;
                 int32_t left, right;
-                unmix(uv[jq], vsrc[jq * 32], mix_res, mix_bits, left, right);
+                unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
                 uint32_t w = __byte_perm((uint32_t)left, (uint32_t)right, 0x5410);
                 if ((uint32_t)q >= cnt) w = 0;
                 ow[q] = w;
@@ -1272,7 +1300,6 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
             slot = seq % RING_SLOTS;
             par = (seq / RING_SLOTS) & 1u;
             uint32_t rel0 = 0;
-            int32_t uv[CHUNK];  // the parked U samples of this chunk's 32 frames
             if (live_any) {
                 // the predictor warp must have parked chunk ck of this pair's U stream (it normally did long ago)
                 if (u_seen < u_first_slot + ck + 1u) {  // warp-uniform; one acquire covers everything published before it
@@ -1283,12 +1310,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
                     __syncwarp();  // orders every lane's reads of the parked samples after lane 0's acquire
                     u_seen = __shfl_sync(FULL_MASK, u_seen, 0);
                 }
-                // U: one coalesced 128-byte line per frame, straight into registers (they land while V is predicted)
-                const uint32_t base_i = ck * CHUNK;
-                const int32_t *up = lc.u_base + (size_t)base_i * 32u + lane;
-#pragma unroll
-                for (int j = 0; j < CHUNK; j++) uv[j] = base_i + (uint32_t)j < lc.frame_length ? __ldcg(up + j * 32) : 0;
-                live_prefetch(sm, lane, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
+                live_prefetch(sm, lane, lc, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
             }
             if (ck > 0) {
                 tw = rt.now();
@@ -1299,9 +1321,9 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncwarp();
                 const int32_t *vsrc = &sm.ring[1][slot][0][lane];
-                if (cfg.bps == 3) live_emit<3>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc, uv);
-                else if (cfg.bps == 2) live_emit<2>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc, uv);
-                else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc, uv);
+                if (cfg.bps == 3) live_emit<3>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+                else if (cfg.bps == 2) live_emit<2>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+                else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
                 __syncwarp();
             }
             mbar_arrive(&sm.empty_bar[1][slot]);
@@ -2362,7 +2384,7 @@ __global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
     while (group < ngroups) {
         if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs_cta, out_bytes, status, group, seq, counters);
         else if (role == 1) predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq);
-        else emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq[1], u_seen);
+        else if (role == 2) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq[1], u_seen);
         __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
         // stage 3 of whatever was not emitted live reuses the window / ring / job memory as its transpose tiles
         EmitArgs ea{packed, offsets, sizes, npackets, scratch_cta, descs_cta, pcm_out, out_stride};

@@ -89,6 +89,16 @@ def test_no_device_fails_loudly_no_cpu_fallback(pkg):
     assert 'no CPU fallback' in str(ei.value)
 
 
+def test_library_decoder_without_device_fails_loudly(pkg):
+    """The multi-track entry point has no CPU fallback either; its argument checks run without a device."""
+    assert pkg.lib.alacb200_library_create(None, 0, None) == pkg.E_ARG
+    if pkg.lib.alacb200_device_count() > 0:
+        pytest.skip('a CUDA device is present')
+    with pytest.raises(pkg.CudaError) as ei:
+        pkg.NewLibraryDecoder((0,))
+    assert 'no CPU fallback' in str(ei.value)
+
+
 def test_error_text_matches_reference_wrapping(pkg):
     assert pkg.format_error(6) == 'decode failed: alac: bitstream overrun'                       # decoder.go:144
     assert pkg.format_error(6 | (2 << 8) | (2 << 12)) == 'decode failed: CPE: entropy decode U: alac: bitstream overrun'
@@ -99,6 +109,7 @@ def test_error_text_matches_reference_wrapping(pkg):
     assert pkg.format_error(8) == 'invalid configuration: alac: unsupported bit depth'
     assert isinstance(pkg.error_from_status(5 | (1 << 8)), pkg.ErrDecode)
     assert isinstance(pkg.error_from_status(1), pkg.ErrConfig)
+    assert pkg.format_error(pkg.ST_IO_TRUNCATED) == 'unexpected EOF'  # io.ReadFull's error, decode.go:172-174
 
 
 def _packets(n=11, size=None):

@@ -11,7 +11,7 @@ else
 fi
 echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu_$TAG.log
 for w in $WORKLOADS; do
-  timeout 900 python bench.py --steps 10 --warmup 3 --workload $w --no-cpu-baseline > gpurun_out/bench_${TAG}_${V}_$w.json 2> gpurun_out/bench_${TAG}_${V}_$w.err
+  timeout 900 python bench.py --steps 10 --warmup 3 --workload $w --no-cpu-baseline --only-main > gpurun_out/bench_${TAG}_${V}_$w.json 2> gpurun_out/bench_${TAG}_${V}_$w.err
   echo "== $V $w rc=$?"; grep -h "alacb200:" gpurun_out/bench_${TAG}_${V}_$w.err | head -1
   python - <<PY
 import json

@@ -9,7 +9,7 @@ fi
 for v in $VARIANTS; do
   if [ "$v" = default ]; then unset ALACB200_LIB; else export ALACB200_LIB=$PWD/saprobe-alac_b200/libalacb200_$v.so; fi
   for w in $WORKLOADS; do
-    timeout 900 python bench.py --steps 10 --warmup 3 --workload $w --no-cpu-baseline > gpurun_out/bench_${TAG}_${v}_$w.json 2> gpurun_out/bench_${TAG}_${v}_$w.err
+    timeout 900 python bench.py --steps 10 --warmup 3 --workload $w --no-cpu-baseline --only-main > gpurun_out/bench_${TAG}_${v}_$w.json 2> gpurun_out/bench_${TAG}_${v}_$w.err
     echo "== $v $w rc=$?"
     python - <<PY
 import json
