@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -60,6 +61,44 @@ struct DevBuf {
         cap = 0;
     }
 };
+// Page-locking host memory costs milliseconds per call, which is most of what NewDecoder / NewPacketDecoder would cost
+// a caller that opens one decoder per file. Released staging buffers are therefore kept (up to a bound) and handed to the
+// next decoder of the process; portable pinned memory serves every device.
+struct PinPool {
+    static constexpr size_t kMaxCached = 3ull << 30;
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> cached;
+    size_t cached_bytes = 0;
+    void *take(size_t bytes, size_t &cap) {
+        std::lock_guard<std::mutex> lock(mu);
+        size_t best = cached.size();
+        for (size_t i = 0; i < cached.size(); i++)
+            if (cached[i].second >= bytes && cached[i].second <= 4 * bytes + (1u << 20) && (best == cached.size() || cached[i].second < cached[best].second))
+                best = i;
+        if (best == cached.size()) return nullptr;
+        void *p = cached[best].first;
+        cap = cached[best].second;
+        cached_bytes -= cap;
+        cached.erase(cached.begin() + (ptrdiff_t)best);
+        return p;
+    }
+    void give(void *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (cached_bytes + cap <= kMaxCached && cached.size() < 256) {
+                cached.emplace_back(p, cap);
+                cached_bytes += cap;
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+};
+PinPool &pin_pool() {
+    static PinPool *pool = new PinPool();  // never destroyed: the CUDA runtime may be gone before static destructors run
+    return *pool;
+}
+
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -67,6 +106,7 @@ struct PinBuf {
         if (bytes <= cap) return true;
         release();
         const size_t want = bytes + bytes / 8 + 256;
+        if ((p = pin_pool().take(want, cap)) != nullptr) return true;
         if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
             g_last_error = "cudaHostAlloc failed";
             cudaGetLastError();
@@ -77,7 +117,7 @@ struct PinBuf {
         return true;
     }
     void release() {
-        if (p) cudaFreeHost(p);
+        if (p) pin_pool().give(p, cap);
         p = nullptr;
         cap = 0;
     }
@@ -760,17 +800,32 @@ int32_t alacb200_library_decode_tracks(alacb200_library *lib, alacb200_track_des
     return rc;
 }
 
+// The public pinned allocator goes through the same pool; the capacity of a block is kept in a small table.
+namespace {
+std::mutex g_pin_mu;
+std::vector<std::pair<void *, size_t>> g_pin_caps;
+}  // namespace
 void *alacb200_pinned_alloc(size_t bytes) {
-    void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
-        g_last_error = "cudaHostAlloc failed";
-        cudaGetLastError();
-        return nullptr;
-    }
-    return p;
+    PinBuf b;
+    if (!b.reserve(bytes ? bytes : 1)) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pin_mu);
+    g_pin_caps.emplace_back(b.p, b.cap);
+    return b.p;
 }
 void alacb200_pinned_free(void *p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    size_t cap = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        for (size_t i = 0; i < g_pin_caps.size(); i++)
+            if (g_pin_caps[i].first == p) {
+                cap = g_pin_caps[i].second;
+                g_pin_caps.erase(g_pin_caps.begin() + (ptrdiff_t)i);
+                break;
+            }
+    }
+    if (cap) pin_pool().give(p, cap);
+    else cudaFreeHost(p);
 }
 
 const char *alacb200_strerror(int32_t status) {

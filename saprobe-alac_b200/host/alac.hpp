@@ -19,6 +19,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -57,6 +58,20 @@ inline PacketConfig ParseMagicCookie(const uint8_t *cookie, size_t len) {
     return cfg;
 }
 inline PacketConfig ParseMagicCookie(const std::vector<uint8_t> &cookie) { return ParseMagicCookie(cookie.data(), cookie.size()); }
+
+// The host side of a big batch is memcpy-bound (packing [][]byte into the pinned arena, copying every packet's PCM into
+// its own fresh buffer): split it over a few host threads. fn(lo, hi) works on the index range [lo, hi).
+template <class F>
+inline void parallel_ranges(size_t n, size_t bytes, F &&fn) {
+    size_t nt = std::min<size_t>({8, std::max<size_t>(1, std::thread::hardware_concurrency()), bytes / (4u << 20) + 1, n ? n : 1});
+    if (nt <= 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back([&, t] { fn(n * t / nt, n * (t + 1) / nt); });
+    for (auto &x : th) x.join();
+}
 
 struct PacketResult {
     std::vector<uint8_t> pcm;     // empty on error
@@ -103,15 +118,19 @@ public:
         uint8_t *in = nullptr, *pcm = nullptr;
         if (alacb200_arena(h_, pos, (uint64_t)n * stride, &in, &pcm) != ALACB200_OK)
             throw Error(ErrKind::Device, 0, std::string("alacb200_arena: ") + alacb200_last_error());
-        for (uint32_t i = 0; i < n; i++)
-            if (sizes[i]) std::memcpy(in + offsets[i], packets[i].first, sizes[i]);
+        parallel_ranges(n, pos, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++)
+                if (sizes[i]) std::memcpy(in + offsets[i], packets[i].first, sizes[i]);
+        });
         std::vector<uint32_t> nbytes(n);
         std::vector<int32_t> status(n);
         DecodeInPlace(in, pos, offsets.data(), sizes.data(), n, pcm, nbytes.data(), status.data());
-        for (uint32_t i = 0; i < n; i++) {
-            if (status[i] == ALACB200_ST_OK) out[i].pcm.assign(pcm + (size_t)i * stride, pcm + (size_t)i * stride + nbytes[i]);
-            else out[i].err.reset(new Error(error_from_status(status[i])));
-        }
+        parallel_ranges(n, (size_t)n * stride, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) {
+                if (status[i] == ALACB200_ST_OK) out[i].pcm.assign(pcm + i * stride, pcm + i * stride + nbytes[i]);
+                else out[i].err.reset(new Error(error_from_status(status[i])));
+            }
+        });
         return out;
     }
 

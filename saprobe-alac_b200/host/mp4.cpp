@@ -66,6 +66,9 @@ Rd read_box(Reader &r, Box &b, std::string &err) {
         err = "mp4: invalid box size";
         return Rd::Bad;
     }
+    // a 64-bit size near INT64_MAX must not overflow offset + size below: a box cannot end behind the image anyway
+    // (the reference only notices when it reads, mp4.go:98-139)
+    if (b.size > INT64_MAX - b.offset) b.size = INT64_MAX - b.offset;
     return Rd::Ok;
 }
 
