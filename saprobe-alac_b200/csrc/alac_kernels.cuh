@@ -182,6 +182,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
 #endif
 }
 
+// ---- hand-over between the role warps ------------------------------------------------------------------------------
+//   full[ring][slot]   entropy -> predictor: the slot holds 32 codes per lane
+//   empty[ring][slot]  predictor (and, ring 1, emit) -> entropy: the slot may be refilled
+//   vdone[slot]        predictor -> emit: ring-1 slot holds decoded V samples
+// mbarriers in shared memory (default). A waiting warp polls -- try_wait comes back within ~10 cycles whatever suspend
+// hint or nanosleep it is given, and the polls are 16 % of the instructions the kernel issues (profiles/r02a) -- but
+// they are free: the same protocol on hardware named barriers (bar.arrive / bar.sync, -DALACB200_NAMED_BARRIERS),
+// where a waiting warp issues nothing at all, is bit-identical and 0.5-1.5 % SLOWER (c2 1.585 vs 1.575 ms, 93 k-packet
+// batch 5.85 vs 5.76 ms). The issue slots were never the limit; the dependent chains of the role warps are.
+#ifdef ALACB200_NAMED_BARRIERS
+// barrier numbers as immediates, so that ptxas reserves the barriers the kernel uses (1..10; 0 is __syncthreads)
+#define ALACB200_BAR_CASES(OP)                                                                                              \
+    switch (id) {                                                                                                          \
+    case 1: asm volatile(OP " 1, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 2: asm volatile(OP " 2, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 3: asm volatile(OP " 3, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 4: asm volatile(OP " 4, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 5: asm volatile(OP " 5, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 6: asm volatile(OP " 6, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 7: asm volatile(OP " 7, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 8: asm volatile(OP " 8, %0;" ::"r"(count) : "memory"); break;                                                     \
+    case 9: asm volatile(OP " 9, %0;" ::"r"(count) : "memory"); break;                                                     \
+    default: asm volatile(OP " 10, %0;" ::"r"(count) : "memory"); break;                                                   \
+    }
+__device__ __forceinline__ void nbar_sync(uint32_t id, uint32_t count) { ALACB200_BAR_CASES("bar.sync") }
+__device__ __forceinline__ void nbar_arrive(uint32_t id, uint32_t count) { ALACB200_BAR_CASES("bar.arrive") }
+#endif
+struct DecShared;
+__device__ __forceinline__ void wait_full(DecShared &sm, int ring, uint32_t seq);
+__device__ __forceinline__ void arrive_full(DecShared &sm, int ring, uint32_t seq);
+__device__ __forceinline__ void wait_empty(DecShared &sm, int ring, uint32_t seq);
+__device__ __forceinline__ void arrive_empty(DecShared &sm, int ring, uint32_t seq);
+__device__ __forceinline__ void wait_vdone(DecShared &sm, uint32_t seq);
+__device__ __forceinline__ void arrive_vdone(DecShared &sm, uint32_t seq);
+
 __device__ unsigned int g_sm_ticket[256];        // per-SM CTA counter (monotonic; only its value mod 4 is used)
 __device__ unsigned int g_sm_entropy_load[256];  // per SM: four 8-bit counts of resident entropy warps, by sub-partition
 // Developer build only (-DALACB200_DEV, `make dev`): per-role clock64 counters, [cta][16] (0..2 E total / wait-empty /
@@ -258,6 +293,25 @@ struct DecShared {
 static_assert(offsetof(DecShared, fifo) == 0 && (FIFO_CHUNKS & (FIFO_CHUNKS - 1)) == 0 && FIFO_CHUNKS >= 16, "lane windows must be aligned to their size");
 static_assert(offsetof(DecShared, ring) % 16 == 0 && offsetof(DecShared, live_shift) % 16 == 0 && offsetof(DecShared, full_bar) % 8 == 0, "alignment");
 
+
+// `seq` is the ring sequence number of the slot (slot = seq % RING_SLOTS, phase = seq / RING_SLOTS)
+#ifdef ALACB200_NAMED_BARRIERS
+__device__ __forceinline__ void wait_full(DecShared &, int ring, uint32_t seq) { nbar_sync(1u + 2u * ring + seq % RING_SLOTS, 64u); }
+__device__ __forceinline__ void arrive_full(DecShared &, int ring, uint32_t seq) { nbar_arrive(1u + 2u * ring + seq % RING_SLOTS, 64u); }
+__device__ __forceinline__ void wait_empty(DecShared &, int ring, uint32_t seq) {
+    if (seq >= RING_SLOTS) nbar_sync(5u + 2u * ring + seq % RING_SLOTS, ring == 1 ? 96u : 64u);
+}
+__device__ __forceinline__ void arrive_empty(DecShared &, int ring, uint32_t seq) { nbar_arrive(5u + 2u * ring + seq % RING_SLOTS, ring == 1 ? 96u : 64u); }
+__device__ __forceinline__ void wait_vdone(DecShared &, uint32_t seq) { nbar_sync(9u + seq % RING_SLOTS, 64u); }
+__device__ __forceinline__ void arrive_vdone(DecShared &, uint32_t seq) { nbar_arrive(9u + seq % RING_SLOTS, 64u); }
+#else
+__device__ __forceinline__ void wait_full(DecShared &sm, int ring, uint32_t seq) { mbar_wait(&sm.full_bar[ring][seq % RING_SLOTS], (seq / RING_SLOTS) & 1u, 200); }
+__device__ __forceinline__ void arrive_full(DecShared &sm, int ring, uint32_t seq) { mbar_arrive(&sm.full_bar[ring][seq % RING_SLOTS]); }
+__device__ __forceinline__ void wait_empty(DecShared &sm, int ring, uint32_t seq) { mbar_wait(&sm.empty_bar[ring][seq % RING_SLOTS], ((seq / RING_SLOTS) & 1u) ^ 1u); }
+__device__ __forceinline__ void arrive_empty(DecShared &sm, int ring, uint32_t seq) { mbar_arrive(&sm.empty_bar[ring][seq % RING_SLOTS]); }
+__device__ __forceinline__ void wait_vdone(DecShared &sm, uint32_t seq) { mbar_wait(&sm.vdone_bar[seq % RING_SLOTS], (seq / RING_SLOTS) & 1u, 400); }
+__device__ __forceinline__ void arrive_vdone(DecShared &sm, uint32_t seq) { mbar_arrive(&sm.vdone_bar[seq % RING_SLOTS]); }
+#endif
 
 // job meta word
 enum : uint32_t { JOB_INACTIVE = 0, JOB_REG = 1, JOB_GENERIC = 2, JOB_EXIT = 3 };  // JOB_EXIT: the group is finished
@@ -620,12 +674,12 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
     for (uint32_t c = 0; c < nchunks; c++) {
         const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
         const unsigned long long tw = rt.now();
-        mbar_wait(&sm.empty_bar[cons][slot], par ^ 1u);
+        wait_empty(sm, cons, seq[cons]);
         rt.add(1, tw);
         uint32_t slot2 = 0;
         if (pair) {
             slot2 = seq[1] % RING_SLOTS;
-            mbar_wait(&sm.empty_bar[1][slot2], ((seq[1] / RING_SLOTS) & 1u) ^ 1u);
+            wait_empty(sm, 1, seq[1]);
         }
         if (c == 0) {
             sm.job[cons][slot][0][lane] = sp.n;
@@ -664,8 +718,8 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                 br.top_up();
                 rt.add(2, tt);
             }
-            // 16 samples without a branch (decode_batch), in the flavour the previous batches call for
             const uint32_t a0 = a_dst + half * (CHUNK / 2) * 128u;  // ring address of the lane's sample: a_dst + 128 j
+            // 16 samples without a branch (decode_batch), in the flavour the previous batches call for
             if (quiet) {
                 const bool saw_run = decode_batch<true>(br, e, bp, pk.size, lim, a0, a_last);
                 quiet = __any_sync(FULL_MASK, saw_run);
@@ -711,10 +765,10 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                 }
             }
         }
-        mbar_arrive(&sm.full_bar[cons][slot]);
+        arrive_full(sm, cons, seq[cons]);
         seq[cons]++;
         if (pair) {
-            mbar_arrive(&sm.full_bar[1][slot2]);
+            arrive_full(sm, 1, seq[1]);
             seq[1]++;
         }
     }
@@ -994,9 +1048,9 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     // the group is finished: tell the predictor warp (ring 0, then ring 1) and, through ring 1, the emit warp
     for (int cons = 0; cons < 2; cons++) {
         const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
-        mbar_wait(&sm.empty_bar[cons][slot], par ^ 1u);
+        wait_empty(sm, cons, seq[cons]);
         sm.job[cons][slot][1][lane] = JOB_EXIT;
-        mbar_arrive(&sm.full_bar[cons][slot]);
+        arrive_full(sm, cons, seq[cons]);
         seq[cons]++;
     }
     if (valid) {
@@ -1277,11 +1331,11 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
         // first slot of a stream: its job
         uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
         unsigned long long tw = rt.now();
-        mbar_wait(&sm.vdone_bar[slot], par, 400);
+        wait_vdone(sm, seq);
         rt.add(1, tw);
         const uint32_t meta = sm.job[1][slot][1][lane];
         if ((meta & 3u) == JOB_EXIT) {  // the group is finished: hand the slot back and leave
-            mbar_arrive(&sm.empty_bar[1][slot]);
+            arrive_empty(sm, 1, seq);
             seq++;
             break;
         }
@@ -1314,7 +1368,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
             }
             if (ck > 0) {
                 tw = rt.now();
-                mbar_wait(&sm.vdone_bar[slot], par, 400);
+                wait_vdone(sm, seq);
                 rt.add(1, tw);
             }
             if (live_any) {
@@ -1326,7 +1380,7 @@ __device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const ui
                 else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
                 __syncwarp();
             }
-            mbar_arrive(&sm.empty_bar[1][slot]);
+            arrive_empty(sm, 1, seq);
             seq++;
         }
         if (live_lane) lc.desc->pad_ = nchunks * CHUNK;  // frames written so far (zeros past the sample count)
@@ -1407,7 +1461,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
-            mbar_wait(&sm.full_bar[cons][slot], par, 200);
+            wait_full(sm, cons, seq);
             rt.add(1, tw);
         }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
@@ -1505,8 +1559,8 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
             outp += 32;
         }
         }
-        if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
-        mbar_arrive(&sm.empty_bar[cons][slot]);
+        if (cons == 1) arrive_vdone(sm, seq);
+        arrive_empty(sm, cons, seq);
         seq++;
         if (lc_publish && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
@@ -1537,7 +1591,7 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
         const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
-            mbar_wait(&sm.full_bar[cons][slot], par, 200);
+            wait_full(sm, cons, seq);
             rt.add(1, tw);
         }
         const int32_t *src = &sm.ring[cons][slot][0][lane];
@@ -1575,8 +1629,8 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
                 dst[(size_t)i * 32u] = x;
             }
         }
-        if (cons == 1) mbar_arrive(&sm.vdone_bar[slot]);
-        mbar_arrive(&sm.empty_bar[cons][slot]);
+        if (cons == 1) arrive_vdone(sm, seq);
+        arrive_empty(sm, cons, seq);
         seq++;
         if (lc_publish && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
@@ -1594,7 +1648,7 @@ __device__ __forceinline__ void stream_escape_pair(DecShared &sm, uint32_t lane,
     for (uint32_t ck = 0; ck < nchunks; ck++) {
         {
             const uint32_t slot = seq[0] % RING_SLOTS, par = (seq[0] / RING_SLOTS) & 1u;
-            if (ck > 0) mbar_wait(&sm.full_bar[0][slot], par, 200);
+            if (ck > 0) wait_full(sm, 0, seq[0]);
             const int32_t *src = &sm.ring[0][slot][0][lane];
             const uint32_t n0 = act0 ? j0.n : 0u;
 #pragma unroll 4
@@ -1602,14 +1656,14 @@ __device__ __forceinline__ void stream_escape_pair(DecShared &sm, uint32_t lane,
                 const uint32_t i = ck * CHUNK + j;
                 if (i < n0) dst0[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
             }
-            mbar_arrive(&sm.empty_bar[0][slot]);
+            arrive_empty(sm, 0, seq[0]);
             seq[0]++;
             if (publish && ((seq[0] & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq[0]);
         }
         {
             const uint32_t slot = seq[1] % RING_SLOTS, par = (seq[1] / RING_SLOTS) & 1u;
             const unsigned long long tw = rt.now();
-            mbar_wait(&sm.full_bar[1][slot], par, 200);
+            wait_full(sm, 1, seq[1]);
             rt.add(1, tw);
             if (ck == 0) {  // the job of the pair's second half
                 const uint32_t meta = sm.job[1][slot][1][lane];
@@ -1623,8 +1677,8 @@ __device__ __forceinline__ void stream_escape_pair(DecShared &sm, uint32_t lane,
                 const uint32_t i = ck * CHUNK + j;
                 if (i < n1) dst1[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
             }
-            mbar_arrive(&sm.vdone_bar[slot]);
-            mbar_arrive(&sm.empty_bar[1][slot]);
+            arrive_vdone(sm, seq[1]);
+            arrive_empty(sm, 1, seq[1]);
             seq[1]++;
         }
     }
@@ -1699,17 +1753,16 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, con
     for (;;) {
         const uint32_t slot = seq[0] % RING_SLOTS, par = (seq[0] / RING_SLOTS) & 1u;
         const unsigned long long tw = rt.now();
-        mbar_wait(&sm.full_bar[0][slot], par, 200);
+        wait_full(sm, 0, seq[0]);
         rt.add(1, tw);
         Job jb;
         const uint32_t meta = read_job(sm, 0, slot, lane, jb);
         if (jb.kind == JOB_EXIT) {  // written for every lane: the group is finished
-            mbar_arrive(&sm.empty_bar[0][slot]);
+            arrive_empty(sm, 0, seq[0]);
             seq[0]++;
-            const uint32_t slot1 = seq[1] % RING_SLOTS, par1 = (seq[1] / RING_SLOTS) & 1u;
-            mbar_wait(&sm.full_bar[1][slot1], par1, 200);  // ring 1's end marker: pass it on to the emit warp
-            mbar_arrive(&sm.vdone_bar[slot1]);
-            mbar_arrive(&sm.empty_bar[1][slot1]);
+            wait_full(sm, 1, seq[1]);  // ring 1's end marker: pass it on to the emit warp
+            arrive_vdone(sm, seq[1]);
+            arrive_empty(sm, 1, seq[1]);
             seq[1]++;
             break;
         }
@@ -1722,9 +1775,9 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, con
         }
         run_stream(sm, lane, 0, seq[0], pk, jb, active, dst, rt, lc);
         if (meta & JOBF_V_FOLLOWS) {
-            const uint32_t slot1 = seq[1] % RING_SLOTS, par1 = (seq[1] / RING_SLOTS) & 1u;
+            const uint32_t slot1 = seq[1] % RING_SLOTS;
             const unsigned long long tw1 = rt.now();
-            mbar_wait(&sm.full_bar[1][slot1], par1, 200);
+            wait_full(sm, 1, seq[1]);
             rt.add(1, tw1);
             Job jv;
             (void)read_job(sm, 1, slot1, lane, jv);
@@ -2331,12 +2384,14 @@ __global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
     if (threadIdx.x == 0) {
+#ifndef ALACB200_NAMED_BARRIERS
         for (int c = 0; c < 2; c++)
             for (int s = 0; s < RING_SLOTS; s++) {
                 mbar_init(&sm.full_bar[c][s], 32);
                 mbar_init(&sm.empty_bar[c][s], c == 1 ? 64 : 32);
             }
         for (int s = 0; s < RING_SLOTS; s++) mbar_init(&sm.vdone_bar[s], 32);
+#endif
         sm.u_chunks_done = 0;
         sm.group = atomicAdd(&counters[0], 1u);
     }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measured PCIe floor for the end-to-end leg: pinned H2D of the compressed bytes and D2H of the PCM, alone and together.
 Alone or under torchrun (one rank per GPU, all ranks copying at the same time): prints per-rank times and the max.
-    python tools/pcie_probe.py [h2d_MiB d2h_MiB]        (defaults: c2's 235 / 346; c3 per rank at N ranks: 1110/N, 3955/N)"""
+    python tools/pcie_probe.py [h2d_MiB d2h_MiB]        (defaults: c2's 235 / 346; c3 per rank at N ranks: 2672/N, 3955/N)"""
 import os, sys, time, torch
 MB = 1 << 20
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))

@@ -55,5 +55,6 @@ fast = sorted(per_sm.items(), key=lambda kv: max(x[1] for x in kv[1]))[:4]
 for sm_, v in fast: print('  fast SM', sm_, [(w, w % 4, round(t,2), round(bz,2)) for w,t,bz in v])
 spp = wl['frames'] / n
 eb=(b[:,0]-b[:,1])/(2*spp)
+
 print(f'E busy cycles/sample over CTAs: min {eb.min():.0f} p10 {np.percentile(eb,10):.0f} median {np.median(eb):.0f} p90 {np.percentile(eb,90):.0f} p97 {np.percentile(eb,97):.0f} max {eb.max():.0f}')
 print(f'per decoded sample (frames/packet = {spp:.0f}): E busy {(b[:,0]-b[:,1]).mean()/(2*spp):.0f} cyc,  P busy {(b[:,3]-b[:,4]).mean()/(2*spp):.0f} cyc,  EMIT busy {(b[:,12]-b[:,13]).mean()/spp:.0f} cyc per frame')
