@@ -182,40 +182,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
 #endif
 }
 
-// ---- hand-over between the role warps ------------------------------------------------------------------------------
-//   full[ring][slot]   entropy -> predictor: the slot holds 32 codes per lane
-//   empty[ring][slot]  predictor (and, ring 1, emit) -> entropy: the slot may be refilled
-//   vdone[slot]        predictor -> emit: ring-1 slot holds decoded V samples
+// ---- hand-over between the two role warps ------------------------------------------------------------------------
+//   full[slot]   entropy -> predictor: the ring slot holds 32 codes per lane
+//   empty[slot]  predictor -> entropy: the slot may be refilled
 // mbarriers in shared memory (default). A waiting warp polls -- try_wait comes back within ~10 cycles whatever suspend
-// hint or nanosleep it is given, and the polls are 16 % of the instructions the kernel issues (profiles/r02a) -- but
-// they are free: the same protocol on hardware named barriers (bar.arrive / bar.sync, -DALACB200_NAMED_BARRIERS),
-// where a waiting warp issues nothing at all, is bit-identical and 0.5-1.5 % SLOWER (c2 1.585 vs 1.575 ms, 93 k-packet
-// batch 5.85 vs 5.76 ms). The issue slots were never the limit; the dependent chains of the role warps are.
+// hint or nanosleep it is given -- but the polls are free: the same protocol on hardware named barriers (bar.arrive /
+// bar.sync, -DALACB200_NAMED_BARRIERS), where a waiting warp issues nothing at all, was bit-identical and 0.5-1.5 %
+// SLOWER when measured on the four-warp form of this kernel (profiles/r02a). The issue slots were never the limit; the
+// dependent chains of the role warps are.
 #ifdef ALACB200_NAMED_BARRIERS
-// barrier numbers as immediates, so that ptxas reserves the barriers the kernel uses (1..10; 0 is __syncthreads)
+// barrier numbers as immediates, so that ptxas reserves the barriers the kernel uses (1..4; 0 is __syncthreads)
 #define ALACB200_BAR_CASES(OP)                                                                                              \
     switch (id) {                                                                                                          \
-    case 1: asm volatile(OP " 1, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 2: asm volatile(OP " 2, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 3: asm volatile(OP " 3, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 4: asm volatile(OP " 4, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 5: asm volatile(OP " 5, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 6: asm volatile(OP " 6, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 7: asm volatile(OP " 7, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 8: asm volatile(OP " 8, %0;" ::"r"(count) : "memory"); break;                                                     \
-    case 9: asm volatile(OP " 9, %0;" ::"r"(count) : "memory"); break;                                                     \
-    default: asm volatile(OP " 10, %0;" ::"r"(count) : "memory"); break;                                                   \
+    case 1: asm volatile(OP " 1, 64;" ::: "memory"); break;                                                                \
+    case 2: asm volatile(OP " 2, 64;" ::: "memory"); break;                                                                \
+    case 3: asm volatile(OP " 3, 64;" ::: "memory"); break;                                                                \
+    default: asm volatile(OP " 4, 64;" ::: "memory"); break;                                                               \
     }
-__device__ __forceinline__ void nbar_sync(uint32_t id, uint32_t count) { ALACB200_BAR_CASES("bar.sync") }
-__device__ __forceinline__ void nbar_arrive(uint32_t id, uint32_t count) { ALACB200_BAR_CASES("bar.arrive") }
+__device__ __forceinline__ void nbar_sync(uint32_t id) { ALACB200_BAR_CASES("bar.sync") }
+__device__ __forceinline__ void nbar_arrive(uint32_t id) { ALACB200_BAR_CASES("bar.arrive") }
 #endif
 struct DecShared;
-__device__ __forceinline__ void wait_full(DecShared &sm, int ring, uint32_t seq);
-__device__ __forceinline__ void arrive_full(DecShared &sm, int ring, uint32_t seq);
-__device__ __forceinline__ void wait_empty(DecShared &sm, int ring, uint32_t seq);
-__device__ __forceinline__ void arrive_empty(DecShared &sm, int ring, uint32_t seq);
-__device__ __forceinline__ void wait_vdone(DecShared &sm, uint32_t seq);
-__device__ __forceinline__ void arrive_vdone(DecShared &sm, uint32_t seq);
+__device__ __forceinline__ void wait_full(DecShared &sm, uint32_t seq);
+__device__ __forceinline__ void arrive_full(DecShared &sm, uint32_t seq);
+__device__ __forceinline__ void wait_empty(DecShared &sm, uint32_t seq);
+__device__ __forceinline__ void arrive_empty(DecShared &sm, uint32_t seq);
 
 __device__ unsigned int g_sm_ticket[256];        // per-SM CTA counter (monotonic; only its value mod 4 is used)
 __device__ unsigned int g_sm_entropy_load[256];  // per SM: four 8-bit counts of resident entropy warps, by sub-partition
@@ -247,43 +238,37 @@ struct RoleTimer {
 #endif
 
 // ---- geometry of one decode CTA ---------------------------------------------------------------------
-// A CTA works on one group of 32 packets at a time (lane = packet); it is persistent and pulls group after group from a
-// counter. The ENTROPY warp hands residual codes, 32 samples at a time, through two shared-memory rings to the PREDICTOR
-// warp: ring 0 carries the mono / U stream of every element, ring 1 the V stream (the streams of a packet follow each
-// other in the bitstream, so one predictor warp serves both rings in turn); the EMIT warp follows ring 1. The fourth
-// warp only joins for the tail. It is there for the hardware's sake: the four warps of a CTA land on the four SM
-// sub-partitions, so every CTA can put its entropy warp on the least loaded scheduler; with three-warp CTAs (five per
-// SM) the warp slots came out uneven over the sub-partitions (one of them got 32 % of the warps) and everything was
-// 9-13 % slower (profiles/r02a).
-#if defined(ALACB200_THREE_WARPS)  // experiment
-constexpr int DEC_THREADS = 96;
-constexpr int CTAS_PER_SM = 5;
-#else
-constexpr int DEC_THREADS = 128;
-constexpr int CTAS_PER_SM = 4;   // 128 threads x 128 registers; ~38 KB of shared memory per CTA
-#endif
+// A CTA is TWO warps working on one group of 32 packets at a time (lane = packet); it is persistent and pulls group after
+// group from a counter. The ENTROPY warp hands residual codes, 32 samples at a time, through a two-slot shared-memory
+// ring to the PREDICTOR warp. The streams of a packet follow each other in the bitstream (V starts where U's last code
+// ends), so one ring and one predictor warp serve them all in turn; for a 2-channel pair the predictor warp also turns
+// every finished V slot (plus the parked U samples and the shift bytes) into PCM right away.
+// Why two warps: every role warp is one dependent chain per lane and issues about once every 4.5 cycles, so a scheduler
+// wants ~4.5 BUSY warps. The four-warp form of this kernel (entropy, predictor, emit, spare: profiles/r02a) kept only
+// ~2.4 of its 4 warps per scheduler busy (issue slots 55 %); with two always-busy warps per group, 64 threads x 128
+// registers and ~27 KB of shared memory, EIGHT groups are resident per SM instead of four.
+constexpr int DEC_THREADS = 64;
+constexpr int CTAS_PER_SM = 8;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
-constexpr int RING_SLOTS = 2;    // ring depth per consumer
+constexpr int RING_SLOTS = 2;    // ring depth
 constexpr int CHUNK = 32;        // samples per ring slot
 constexpr int FIFO_CHUNKS = 16;  // 16-byte chunks of compressed bytes staged per lane (256 B window)
 constexpr int LIVE_SHIFT_CHUNKS = 10;  // 16-byte chunks covering 32 frames x 2 channels x 2 shift bytes at any alignment
+constexpr int JOB_WORDS = 6;     // per lane and stream: n, meta, coefficient bit position, nmax, live-emit word, shift bit position
 
 struct DecShared {
     // Compressed bytes staged by cp.async: a 256-byte window per lane, [lane][chunk ^ (lane & 7)]. The window of a lane
     // starts on a 256-byte boundary of the shared address space (the struct sits at a 1024-byte aligned base), so the
     // address of a word is one LOP3: (byte offset & 0xfc) ^ window base; the XOR spreads the lanes over the banks.
     uint4 fifo[32][FIFO_CHUNKS];
-    int32_t ring[2][RING_SLOTS][CHUNK][32];  // residuals, [consumer][slot][sample][lane]  (16 KB)
-    uint32_t job[2][RING_SLOTS][8][32];      // per stream, with its first chunk: n, meta, coef bit position, nmax,
-                                             // live-emit word, shift bit position, first consumer-0 slot of the U stream
+    int32_t ring[RING_SLOTS][CHUNK][32];     // residual codes (then, for a live pair, decoded V samples), [slot][sample][lane]
+    uint32_t job[RING_SLOTS][JOB_WORDS][32];  // what the stream is, with its first slot
     // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
     int32_t live_u[CHUNK][32];
     uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
     // barriers last: stage 3 reuses everything in front of them as its transpose tiles
-    uint64_t full_bar[2][RING_SLOTS];
-    uint64_t empty_bar[2][RING_SLOTS];  // ring 1's slots are released by the predictor warp AND the emit warp
-    uint64_t vdone_bar[RING_SLOTS];     // predictor warp -> emit warp: the ring-1 slot now holds decoded V samples
-    volatile uint32_t u_chunks_done;    // ring-0 slots the predictor warp has finished and parked (release/acquire by fences)
+    uint64_t full_bar[RING_SLOTS];
+    uint64_t empty_bar[RING_SLOTS];
     uint32_t group;                     // packet group this CTA works on
     uint32_t next_group;                // the one after it, fetched by the entropy warp while the group is decoded
     uint32_t entropy_smsp;              // sub-partition of this CTA's entropy warp
@@ -292,32 +277,28 @@ struct DecShared {
 };
 static_assert(offsetof(DecShared, fifo) == 0 && (FIFO_CHUNKS & (FIFO_CHUNKS - 1)) == 0 && FIFO_CHUNKS >= 16, "lane windows must be aligned to their size");
 static_assert(offsetof(DecShared, ring) % 16 == 0 && offsetof(DecShared, live_shift) % 16 == 0 && offsetof(DecShared, full_bar) % 8 == 0, "alignment");
-
+static_assert(sizeof(DecShared) + 1024 <= (228 * 1024) / CTAS_PER_SM, "eight CTAs per SM");
 
 // `seq` is the ring sequence number of the slot (slot = seq % RING_SLOTS, phase = seq / RING_SLOTS)
 #ifdef ALACB200_NAMED_BARRIERS
-__device__ __forceinline__ void wait_full(DecShared &, int ring, uint32_t seq) { nbar_sync(1u + 2u * ring + seq % RING_SLOTS, 64u); }
-__device__ __forceinline__ void arrive_full(DecShared &, int ring, uint32_t seq) { nbar_arrive(1u + 2u * ring + seq % RING_SLOTS, 64u); }
-__device__ __forceinline__ void wait_empty(DecShared &, int ring, uint32_t seq) {
-    if (seq >= RING_SLOTS) nbar_sync(5u + 2u * ring + seq % RING_SLOTS, ring == 1 ? 96u : 64u);
+__device__ __forceinline__ void wait_full(DecShared &, uint32_t seq) { nbar_sync(1u + seq % RING_SLOTS); }
+__device__ __forceinline__ void arrive_full(DecShared &, uint32_t seq) { nbar_arrive(1u + seq % RING_SLOTS); }
+__device__ __forceinline__ void wait_empty(DecShared &, uint32_t seq) {  // the first RING_SLOTS uses find the ring empty
+    if (seq >= RING_SLOTS) nbar_sync(3u + seq % RING_SLOTS);
 }
-__device__ __forceinline__ void arrive_empty(DecShared &, int ring, uint32_t seq) { nbar_arrive(5u + 2u * ring + seq % RING_SLOTS, ring == 1 ? 96u : 64u); }
-__device__ __forceinline__ void wait_vdone(DecShared &, uint32_t seq) { nbar_sync(9u + seq % RING_SLOTS, 64u); }
-__device__ __forceinline__ void arrive_vdone(DecShared &, uint32_t seq) { nbar_arrive(9u + seq % RING_SLOTS, 64u); }
+__device__ __forceinline__ void arrive_empty(DecShared &, uint32_t seq) { nbar_arrive(3u + seq % RING_SLOTS); }
 #else
-__device__ __forceinline__ void wait_full(DecShared &sm, int ring, uint32_t seq) { mbar_wait(&sm.full_bar[ring][seq % RING_SLOTS], (seq / RING_SLOTS) & 1u, 200); }
-__device__ __forceinline__ void arrive_full(DecShared &sm, int ring, uint32_t seq) { mbar_arrive(&sm.full_bar[ring][seq % RING_SLOTS]); }
-__device__ __forceinline__ void wait_empty(DecShared &sm, int ring, uint32_t seq) { mbar_wait(&sm.empty_bar[ring][seq % RING_SLOTS], ((seq / RING_SLOTS) & 1u) ^ 1u); }
-__device__ __forceinline__ void arrive_empty(DecShared &sm, int ring, uint32_t seq) { mbar_arrive(&sm.empty_bar[ring][seq % RING_SLOTS]); }
-__device__ __forceinline__ void wait_vdone(DecShared &sm, uint32_t seq) { mbar_wait(&sm.vdone_bar[seq % RING_SLOTS], (seq / RING_SLOTS) & 1u, 400); }
-__device__ __forceinline__ void arrive_vdone(DecShared &sm, uint32_t seq) { mbar_arrive(&sm.vdone_bar[seq % RING_SLOTS]); }
+__device__ __forceinline__ void wait_full(DecShared &sm, uint32_t seq) { mbar_wait(&sm.full_bar[seq % RING_SLOTS], (seq / RING_SLOTS) & 1u, 200); }
+__device__ __forceinline__ void arrive_full(DecShared &sm, uint32_t seq) { mbar_arrive(&sm.full_bar[seq % RING_SLOTS]); }
+__device__ __forceinline__ void wait_empty(DecShared &sm, uint32_t seq) { mbar_wait(&sm.empty_bar[seq % RING_SLOTS], ((seq / RING_SLOTS) & 1u) ^ 1u); }
+__device__ __forceinline__ void arrive_empty(DecShared &sm, uint32_t seq) { mbar_arrive(&sm.empty_bar[seq % RING_SLOTS]); }
 #endif
 
 // job meta word
 enum : uint32_t { JOB_INACTIVE = 0, JOB_REG = 1, JOB_GENERIC = 2, JOB_EXIT = 3 };  // JOB_EXIT: the group is finished
-// warp-uniform flags in the meta word of a ring-0 job: a V stream follows on ring 1 / ring 1 carries the other half of
-// an interleaved escape pair (the one predictor warp has to know where its next stream arrives)
-enum : uint32_t { JOBF_V_FOLLOWS = 1u << 24, JOBF_PAIR = 1u << 25 };
+// warp-uniform flag in the meta word of a job: the two halves of an interleaved escape pair arrive in alternating slots
+// (this job is the first half's, the next slot carries the second half's)
+enum : uint32_t { JOBF_PAIR = 1u << 25 };
 __device__ __forceinline__ uint32_t job_meta(uint32_t kind, uint32_t order, uint32_t den, uint32_t mode, uint32_t chan_bits,
                                              uint32_t slot) {
     return kind | (order << 2) | (den << 7) | ((mode != 0 ? 1u : 0u) << 11) | (chan_bits << 12) | (slot << 18);
@@ -582,7 +563,6 @@ struct StreamSpec {
     uint32_t coef_bitpos;  // where the consumer finds the 16-bit coefficients
     uint32_t live;         // V of a pair in a 2-channel stream: bit 31 set, mixBits | mixRes<<8 | bytesShifted<<16
     uint32_t shift_bitpos;
-    uint32_t u_first_slot;    // consumer-0 sequence number of the first ring slot of this pair's U stream
 };
 
 // ---- 16 samples without a branch ------------------------------------------------------------------------------
@@ -593,12 +573,16 @@ struct StreamSpec {
 // other flavour, ...) FREEZES: it is put into a pseudo zero run whose length counts the samples it sits out, and
 // catches up in the general code after the batch. The QUIET flavour has the longer dependency chain (two codes per
 // sample) and is only used while run-length codes keep appearing; it returns whether this lane saw one.
+#ifndef ALACB200_EUNROLL
+#define ALACB200_EUNROLL 2  // was 4 while four groups shared an SM; with eight, the loop's footprint in the L0 I-cache counts more
+#endif
+constexpr int E_UNROLL = ALACB200_EUNROLL;
 template <bool QUIET>
 __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t &bp, uint32_t pk_size, uint32_t lim,
                                              uint32_t a0, uint32_t a_last) {
     bool saw_run = false;
     const uint32_t a_end = a0 + (CHUNK / 2) * 128u;
-#pragma unroll (QUIET ? 2 : 4)
+#pragma unroll (QUIET ? 2 : E_UNROLL)
     for (uint32_t aj = a0; aj != a_end; aj += 128u) {
         const uint32_t n0 = br.load(br.qo);  // the word after lo
         const uint32_t w = br.window();
@@ -650,12 +634,12 @@ __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t
     return saw_run;
 }
 
-// Produce one stream for consumer `cons`: ceil(nmax/32) ring slots (at least one: it carries the job).
-// For an interleaved escape pair both consumers' slots are filled in the same pass.
-__device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int cons, uint32_t *seq, const Packet &pk,
+// Produce one stream: ceil(nmax/32) ring slots (at least one: it carries the job). The two halves of an interleaved
+// escape pair are filled in the same pass and go out in alternating slots (first half, second half, first half, ...).
+__device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk,
                                                const DevConfig &cfg, BitReader &br, uint32_t &bp, int32_t &st,
-                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, uint32_t flags,
-                                               bool &quiet, RoleTimer &rt) {
+                                               const StreamSpec &sp, const StreamSpec &sp2, bool pair, bool &quiet,
+                                               RoleTimer &rt) {
     bool active = sp.active && st == ST_OK;
     const uint32_t nmax = __reduce_max_sync(FULL_MASK, active ? sp.n : 0u);
     const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
@@ -672,33 +656,28 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
     uint32_t busy = (sp.escape ? BUSY_ESCAPE : 0u) | (cfg.kb > 22u ? BUSY_LONG_CODES : 0u) | (active ? 0u : BUSY_DEAD);
 #pragma unroll 1
     for (uint32_t c = 0; c < nchunks; c++) {
-        const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
+        const uint32_t slot = seq % RING_SLOTS, slot2 = (seq + 1u) % RING_SLOTS;
         const unsigned long long tw = rt.now();
-        wait_empty(sm, cons, seq[cons]);
+        wait_empty(sm, seq);
+        if (pair) wait_empty(sm, seq + 1u);
         rt.add(1, tw);
-        uint32_t slot2 = 0;
-        if (pair) {
-            slot2 = seq[1] % RING_SLOTS;
-            wait_empty(sm, 1, seq[1]);
-        }
         if (c == 0) {
-            sm.job[cons][slot][0][lane] = sp.n;
-            sm.job[cons][slot][1][lane] = (active ? sp.meta : (uint32_t)JOB_INACTIVE) | flags;
-            sm.job[cons][slot][2][lane] = sp.coef_bitpos;
-            sm.job[cons][slot][3][lane] = nmax;
-            sm.job[cons][slot][4][lane] = active ? sp.live : 0u;
-            sm.job[cons][slot][5][lane] = sp.shift_bitpos;
-            sm.job[cons][slot][6][lane] = sp.u_first_slot;
+            sm.job[slot][0][lane] = sp.n;
+            sm.job[slot][1][lane] = (active ? sp.meta : (uint32_t)JOB_INACTIVE) | (pair ? (uint32_t)JOBF_PAIR : 0u);
+            sm.job[slot][2][lane] = sp.coef_bitpos;
+            sm.job[slot][3][lane] = nmax;
+            sm.job[slot][4][lane] = active ? sp.live : 0u;
+            sm.job[slot][5][lane] = sp.shift_bitpos;
             if (pair) {
-                sm.job[1][slot2][0][lane] = sp2.n;
-                sm.job[1][slot2][1][lane] = active ? sp2.meta : (uint32_t)JOB_INACTIVE;
-                sm.job[1][slot2][2][lane] = sp2.coef_bitpos;
-                sm.job[1][slot2][3][lane] = nmax;
-                sm.job[1][slot2][4][lane] = 0u;  // escape pairs arrive interleaved: not emitted live
+                sm.job[slot2][0][lane] = sp2.n;
+                sm.job[slot2][1][lane] = active ? sp2.meta : (uint32_t)JOB_INACTIVE;
+                sm.job[slot2][2][lane] = sp2.coef_bitpos;
+                sm.job[slot2][3][lane] = nmax;
+                sm.job[slot2][4][lane] = 0u;  // escape pairs arrive interleaved: not emitted live
             }
         }
-        const uint32_t a_dst = smem_u32(&sm.ring[cons][slot][0][lane]);
-        const uint32_t a_pair = smem_u32(&sm.ring[1][slot2][0][lane]) - a_dst;
+        const uint32_t a_dst = smem_u32(&sm.ring[slot][0][lane]);
+        const uint32_t a_pair = smem_u32(&sm.ring[slot2][0][lane]) - a_dst;
         // samples of this lane inside this chunk
         const uint32_t base_i = c * CHUNK;
         const uint32_t cnt = (active && sp.n > base_i) ? min((uint32_t)CHUNK, sp.n - base_i) : 0u;
@@ -765,11 +744,11 @@ __device__ __forceinline__ void produce_stream(DecShared &sm, uint32_t lane, int
                 }
             }
         }
-        arrive_full(sm, cons, seq[cons]);
-        seq[cons]++;
+        arrive_full(sm, seq);
+        seq++;
         if (pair) {
-            arrive_full(sm, 1, seq[1]);
-            seq[1]++;
+            arrive_full(sm, seq);
+            seq++;
         }
     }
 }
@@ -891,13 +870,13 @@ __device__ __forceinline__ void parse_to_next_element(const Packet &pk, const De
     }
 }
 
-// One group of 32 packets. `seq` (ring sequence numbers) lives across the groups of a persistent CTA; `descs` are the
+// One group of 32 packets. `seq` (ring sequence number) lives across the groups of a persistent CTA; `descs` are the
 // CTA's own 32 descriptors.
 __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
                                              const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
                                              uint32_t npackets, const DevConfig &cfg, PacketDesc *__restrict__ descs,
                                              uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status, uint32_t group,
-                                             uint32_t *seq, uint32_t *__restrict__ counters) {
+                                             uint32_t &seq, uint32_t *__restrict__ counters) {
     // the group after this one: fetched now, read by the whole CTA after the group's barrier
     if (lane == 0) sm.next_group = atomicAdd(&counters[0], 1u);
     const uint32_t pidx = group * 32u + lane;
@@ -912,7 +891,6 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
     int32_t st = ST_OK;
     bool parsing = valid;
     if (valid && pk.size > 0x0FFFFFFFu) { st = ST_REF_PANIC; parsing = false; }  // bit positions are 32-bit here
-    uint32_t u_first = 0;    // ring-0 sequence number at which the current element's U / mono stream starts
     bool quiet = false;      // warp-uniform: run-length codes keep appearing, decode them in line (decode_batch<true>)
     BitReader br;
     br.fifo = fifo_addr;
@@ -929,8 +907,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         StreamSpec s0, s1;
         s0.live = s1.live = 0;
         s0.shift_bitpos = s1.shift_bitpos = 0;
-        s0.u_first_slot = s1.u_first_slot = 0;
-        // 2-channel streams whose 32 packets all carry one compressed pair: the V predictor warp emits PCM itself
+        // 2-channel streams whose 32 packets all carry one compressed pair: the predictor warp emits PCM itself
         #ifdef ALACB200_DEV
         const bool live_allowed = !(g_debug_flags & 1u);
 #else
@@ -969,7 +946,6 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         // compressed elements: pass 0 = U (or mono), pass 1 = V; escape pairs: pass 2, one interleaved sweep
         // feeding both consumers (decoder.go:513-533)
         uint32_t bp = cur.bp;
-        const bool v_follows = __any_sync(FULL_MASK, h.have && h.stereo && !h.escape);  // pass 1 will run
 #pragma unroll 1
         for (int pass = 0; pass < 3; pass++) {
             const bool esc_pair = h.have && h.stereo && h.escape;
@@ -986,14 +962,11 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                     st = ST_REF_PANIC | ctx;
             }
             const int32_t before = st;
-            if (pass != 1) u_first = seq[0];
             if (pass == 1 && live_round) {
                 a.live = 0x80000000u | (h.mix_bits & 0xffu) | (((uint32_t)h.mix_res & 0xffu) << 8) | (h.shift << 16);
                 a.shift_bitpos = h.shift_bitpos;
-                a.u_first_slot = u_first;
             }
-            const uint32_t flags = pass == 0 ? (v_follows ? (uint32_t)JOBF_V_FOLLOWS : 0u) : pass == 2 ? (uint32_t)JOBF_PAIR : 0u;
-            produce_stream(sm, lane, pass == 1 ? 1 : 0, seq, pk, cfg, br, bp, st, a, s1, pass == 2, flags, quiet, rt);
+            produce_stream(sm, lane, seq, pk, cfg, br, bp, st, a, s1, pass == 2, quiet, rt);
             if (act && before == ST_OK && st != ST_OK) {  // an entropy error of this stream: tag it (decoder.go:303, :463, :478)
                 if ((st & 0xff) == ST_REF_PANIC) st |= ctx;
                 else st |= ctx | ((pass == 1 ? ENT_V : h.stereo ? ENT_U : ENT_MONO) << 12);
@@ -1025,7 +998,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
                     op.shift = (uint8_t)(h.escape ? 0u : h.shift);
                     op.mix_bits = (uint8_t)h.mix_bits;
                     op.mix_res = (int8_t)h.mix_res;
-                    op.pad_ = live_round ? 1 : 0;  // already written to pcm_out by the V predictor warp
+                    op.pad_ = live_round ? 1 : 0;  // already written to pcm_out by the predictor warp
                     desc->ops[nops++] = op;
                     ns = h.n;
                     chan_idx += h.stereo ? 2u : 1u;
@@ -1045,14 +1018,11 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
         rt.slot[11] = ((unsigned long long)smid << 8) | wid;
     }
 #endif
-    // the group is finished: tell the predictor warp (ring 0, then ring 1) and, through ring 1, the emit warp
-    for (int cons = 0; cons < 2; cons++) {
-        const uint32_t slot = seq[cons] % RING_SLOTS, par = (seq[cons] / RING_SLOTS) & 1u;
-        wait_empty(sm, cons, seq[cons]);
-        sm.job[cons][slot][1][lane] = JOB_EXIT;
-        arrive_full(sm, cons, seq[cons]);
-        seq[cons]++;
-    }
+    // the group is finished: tell the predictor warp
+    wait_empty(sm, seq);
+    sm.job[seq % RING_SLOTS][1][lane] = JOB_EXIT;
+    arrive_full(sm, seq);
+    seq++;
     if (valid) {
         desc->status = st;
         desc->n_final = ns;
@@ -1073,7 +1043,7 @@ __device__ __forceinline__ int32_t delta_step(bool on, int32_t &prev, int32_t r,
 }
 
 struct Job {
-    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax, live, shift_bitpos, u_first_slot;
+    uint32_t kind, order, den, mode, chan_bits, slot, n, coef_bitpos, nmax, live, shift_bitpos;
 };
 
 // sb (8 or 16) bits at bit offset `rel` of a staged shift row (bytes in stream order, 32-bit words as loaded)
@@ -1085,14 +1055,16 @@ __device__ __forceinline__ uint32_t shift_field(const uint32_t *row_words, uint3
     return win >> (32u - sb);
 }
 
-// What the V predictor warp needs to emit PCM itself (2-channel streams).
+// What the predictor warp needs to emit PCM itself (2-channel streams).
 struct LiveCtx {
     const int32_t *u_base;  // parked U samples of this group, [sample][lane]
     uint8_t *slot;          // this lane's packet slot in pcm_out
     PacketDesc *desc;
     uint32_t frame_length, bps, bit_depth;
     bool vec_ok, enabled;
-    bool publish;  // U / mono predictor warp of a 2-channel stream: the emit warp reads its parked samples back
+    // of the V stream being emitted:
+    bool live_lane;         // this lane's pair is emitted live
+    uint32_t n_lane, live_word, sb, shift_bitpos;
 };
 
 // Start fetching what the emission of chunk `ck` needs: the parked U samples of the 32 frames (one 4 KB block,
@@ -1213,13 +1185,13 @@ __device__ __forceinline__ void unmix(int32_t u, int32_t v, int32_t mix_res, uin
     right = mix_res != 0 ? l - v : v;
 }
 
-// Store the packed words of 16 frames (NW4 x 16 bytes) to the lane's packet slot.
-template <int NW4>
+// Store the packed words of FRAMES frames (NW4 x 16 bytes) to the lane's packet slot.
+template <int NW4, int FRAMES>
 __device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint32_t fb, const uint32_t *ow, bool live_lane) {
     if (!live_lane) return;
     uint8_t *dst = lc.slot + (size_t)f0 * fb;
-    const uint32_t frames_here = min(16u, lc.frame_length - f0);
-    if (frames_here == 16u && lc.vec_ok) {
+    const uint32_t frames_here = min((uint32_t)FRAMES, lc.frame_length - f0);
+    if (frames_here == (uint32_t)FRAMES && lc.vec_ok) {
 #pragma unroll
         for (int k = 0; k < NW4; k++)
             reinterpret_cast<uint4 *>(dst)[k] = make_uint4(ow[4 * k], ow[4 * k + 1], ow[4 * k + 2], ow[4 * k + 3]);
@@ -1235,10 +1207,12 @@ __device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint
     }
 }
 
-// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u, shift bytes from live_shift; two
-// batches of 16 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
+// Emit the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u, shift bytes from live_shift; four
+// batches of 8 frames, each leaving as 128-bit stores to the lane's own packet slot (WriteStereo16/24, matrix.go:30-142).
 // The two shapes real streams have -- 16-bit, and 24-bit with one shifted byte -- are packed with byte permutes
-// (3 PRMT per 2 frames); everything else takes the generic path.
+// (3 PRMT per 2 frames); everything else takes the generic path. The batch loop is NOT unrolled: this code runs once per
+// ring slot between two stretches of the predictor loop, and what it evicts from the instruction cache costs more than
+// the loop overhead.
 template <int BPS>
 __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
@@ -1252,27 +1226,27 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
     const uint32_t mix_bits = live_word & 0xffu;
     const uint32_t *shrow = reinterpret_cast<const uint32_t *>(&sm.live_shift[lane][0]);
 #pragma unroll 1
-    for (uint32_t half = 0; half < 2; half++) {
-        const uint32_t f0 = ck * CHUNK + half * 16u;
+    for (uint32_t b8 = 0; b8 < CHUNK / 8; b8++) {
+        const uint32_t f0 = ck * CHUNK + b8 * 8u;
         if (f0 >= lc.frame_length) break;
-        const uint32_t cnt = n_lane > f0 ? min(16u, n_lane - f0) : 0u;
+        const uint32_t cnt = n_lane > f0 ? min(8u, n_lane - f0) : 0u;
         if (BPS == 3) {
-            // 16 frames x (1 byte L + 1 byte R) of shift data: 9 windows of 32 bits, two frames each
-            const uint32_t rel = rel0 + half * 256u;
+            // 8 frames x (1 byte L + 1 byte R) of shift data: 4 windows of 32 bits, two frames each
+            const uint32_t rel = rel0 + b8 * 128u;
             const uint32_t wb = rel >> 5, bo = rel & 31u;
-            uint32_t W[10], S[9];
+            uint32_t W[5], S[4];
 #pragma unroll
-            for (int k = 0; k < 10; k++) W[k] = __byte_perm(shrow[wb + k], 0, 0x0123);
+            for (int k = 0; k < 5; k++) W[k] = __byte_perm(shrow[wb + k], 0, 0x0123);
 #pragma unroll
-            for (int k = 0; k < 9; k++) S[k] = __funnelshift_l(W[k + 1], W[k], bo);
-            uint32_t ow[24];
+            for (int k = 0; k < 4; k++) S[k] = __funnelshift_l(W[k + 1], W[k], bo);
+            uint32_t ow[12];
 #pragma unroll
-            for (int pr = 0; pr < 8; pr++) {
+            for (int pr = 0; pr < 4; pr++) {
                 uint32_t x24[4];
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int q = 2 * pr + e;
-                    const uint32_t jq = half * 16u + (uint32_t)q;
+                    const uint32_t jq = b8 * 8u + (uint32_t)q;
                     int32_t left, right;
                     unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
                     // (x << 8) | shift byte (matrix.go:132-135): frame 2k sits in the upper half of S[k], 2k+1 in the lower
@@ -1286,117 +1260,34 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
                 ow[3 * pr + 1] = __byte_perm(x24[1], x24[2], 0x5421);  // R0 R0 L1 L1
                 ow[3 * pr + 2] = __byte_perm(x24[2], x24[3], 0x6542);  // L1 R1 R1 R1
             }
-            store_batch<6>(lc, f0, 6u, ow, live_lane);
+            store_batch<3, 8>(lc, f0, 6u, ow, live_lane);
         } else {
-            uint32_t ow[16];
+            uint32_t ow[8];
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const uint32_t jq = half * 16u + (uint32_t)q;
+            for (int q = 0; q < 8; q++) {
+                const uint32_t jq = b8 * 8u + (uint32_t)q;
                 int32_t left, right;
                 unmix(sm.live_u[jq][lane], vsrc[jq * 32u], mix_res, mix_bits, left, right);
                 uint32_t w = __byte_perm((uint32_t)left, (uint32_t)right, 0x5410);
                 if ((uint32_t)q >= cnt) w = 0;
                 ow[q] = w;
             }
-            store_batch<4>(lc, f0, 4u, ow, live_lane);
+            store_batch<2, 8>(lc, f0, 4u, ow, live_lane);
         }
     }
 }
 
-// EMIT warp (2-channel streams): follows ring 1 behind the predictor warp. For a live stream it turns every slot (decoded
-// V samples) plus the parked U samples and the shift bytes into interleaved PCM in pcm_out; for any other stream it only
-// hands the slot back. It is the last reader of ring 1's slots. `seq` / `u_seen` live across the groups of the CTA.
-__device__ __forceinline__ void emit_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
-                                          const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
-                                          uint32_t npackets, const DevConfig &cfg, const int32_t *__restrict__ scratch,
-                                          PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out, uint64_t out_stride,
-                                          uint32_t group, uint32_t &seq, uint32_t &u_seen) {
-    const uint32_t pidx = group * 32u + lane;
-    const bool valid = pidx < npackets;
-    Packet pk{packed, 0};
-    if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
-    LiveCtx lc;
-    lc.u_base = scratch;  // slot 0 of the CTA's scratch = U
-    lc.slot = pcm_out + (size_t)pidx * out_stride;
-    lc.desc = descs + lane;
-    lc.frame_length = cfg.frame_length;
-    lc.bps = cfg.bps;
-    lc.bit_depth = cfg.bit_depth;
-    lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
-    lc.enabled = true;
-    RoleTimer rt(lane, 12);
-    const unsigned long long t_start = rt.now();
-#pragma unroll 1
-    for (;;) {
-        // first slot of a stream: its job
-        uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
-        unsigned long long tw = rt.now();
-        wait_vdone(sm, seq);
-        rt.add(1, tw);
-        const uint32_t meta = sm.job[1][slot][1][lane];
-        if ((meta & 3u) == JOB_EXIT) {  // the group is finished: hand the slot back and leave
-            arrive_empty(sm, 1, seq);
-            seq++;
-            break;
-        }
-        const uint32_t n = sm.job[1][slot][0][lane];
-        const uint32_t nmax = __shfl_sync(FULL_MASK, sm.job[1][slot][3][lane], 0);
-        const uint32_t live_word = sm.job[1][slot][4][lane];
-        const uint32_t shift_bitpos = sm.job[1][slot][5][lane];
-        const uint32_t u_first_slot = __shfl_sync(FULL_MASK, sm.job[1][slot][6][lane], 0);
-        const bool live_lane = valid && (meta & 3u) != JOB_INACTIVE && (live_word >> 31) != 0u;
-        const bool live_any = __any_sync(FULL_MASK, live_lane);
-        const uint32_t n_lane = live_lane ? n : 0u;
-        const uint32_t sb = (cfg.bit_depth == 24 || cfg.bit_depth == 32) ? ((live_word >> 16) & 3u) * 8u : 0u;
-        const uint32_t nchunks = max(1u, (nmax + CHUNK - 1) / CHUNK);
-#pragma unroll 1
-        for (uint32_t ck = 0; ck < nchunks; ck++) {
-            slot = seq % RING_SLOTS;
-            par = (seq / RING_SLOTS) & 1u;
-            uint32_t rel0 = 0;
-            if (live_any) {
-                // the predictor warp must have parked chunk ck of this pair's U stream (it normally did long ago)
-                if (u_seen < u_first_slot + ck + 1u) {  // warp-uniform; one acquire covers everything published before it
-                    if (lane == 0) {
-                        while ((u_seen = sm.u_chunks_done) < u_first_slot + ck + 1u) __nanosleep(64);
-                        __threadfence_block();
-                    }
-                    __syncwarp();  // orders every lane's reads of the parked samples after lane 0's acquire
-                    u_seen = __shfl_sync(FULL_MASK, u_seen, 0);
-                }
-                live_prefetch(sm, lane, lc, pk, ck, live_lane, n_lane, sb, shift_bitpos, rel0);
-            }
-            if (ck > 0) {
-                tw = rt.now();
-                wait_vdone(sm, seq);
-                rt.add(1, tw);
-            }
-            if (live_any) {
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncwarp();
-                const int32_t *vsrc = &sm.ring[1][slot][0][lane];
-                if (cfg.bps == 3) live_emit<3>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
-                else if (cfg.bps == 2) live_emit<2>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
-                else live_emit<4>(sm, lane, lc, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
-                __syncwarp();
-            }
-            arrive_empty(sm, 1, seq);
-            seq++;
-        }
-        if (live_lane) lc.desc->pad_ = nchunks * CHUNK;  // frames written so far (zeros past the sample count)
-    }
-    rt.add(0, t_start);
-    rt.flush(2);
-}
-
-// The U / mono predictor warp has parked everything up to ring slot `seq` of its consumer: release it to the emit warp,
-// which reads the parked samples back through L2 (cp.async.cg).
-__device__ __forceinline__ void publish_parked(DecShared &sm, uint32_t lane, uint32_t seq) {
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();  // writer and reader share the CTA (and the SM's path to L2, which the reader's cp.async.cg takes)
-        sm.u_chunks_done = seq;
-    }
+// Stage 3 of one ring slot of a live pair, by the predictor warp itself: the slot holds the decoded V samples, live_u /
+// live_shift were requested (live_prefetch) before the slot was predicted. One copy of the packing code for every
+// instantiation of the predictor loop.
+__device__ __noinline__ void live_chunk_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, uint32_t rel0,
+                                             const int32_t *vsrc) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();  // live_u is fetched cooperatively
+    if (lc.bps == 3) live_emit<3>(sm, lane, lc, ck, lc.live_lane, lc.n_lane, lc.live_word, lc.sb, rel0, vsrc);
+    else if (lc.bps == 2) live_emit<2>(sm, lane, lc, ck, lc.live_lane, lc.n_lane, lc.live_word, lc.sb, rel0, vsrc);
+    else live_emit<4>(sm, lane, lc, ck, lc.live_lane, lc.n_lane, lc.live_word, lc.sb, rel0, vsrc);
+    __syncwarp();  // live_u / live_shift are free for the next slot's requests
 }
 
 // sign-extend the low `bits` (1..32) of v: (v << (32 - bits)) >> (32 - bits) in one SGXT
@@ -1413,18 +1304,19 @@ __device__ __forceinline__ void mad_if(int32_t &c, int32_t a, int32_t b, bool p)
 // Register predictor: orders 4/5/6/8 with int32 coefficients (unpcBlock4/5/6/8, predictor.go:99-618), plus
 // order 0 (copy, also escape pass-through) and order 31 (running sum), predictor.go:55-72. T = taps kept;
 // a lane whose order is below T runs with its upper taps' history differences forced to zero, which keeps
-// their coefficients at zero and their LMS terms at zero. The body is branch-free; only the store is predicated.
-template <int T, bool MODE, bool LIVE>
-__device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
+// their coefficients at zero and their LMS terms at zero. The body is branch-free. The decoded samples replace the codes
+// in the ring slot; when the slot is done they leave as PCM (`live`: the V stream of a 2-channel pair, live_chunk_emit)
+// or are parked in the scratch. One loop body for both kinds of stream: the U and V streams of a packet alternate in
+// this warp, and every KB of hot code less is instruction-cache hits for the 16 role warps of the SM (the 6 KB L0 of a
+// scheduler holds the loops of its entropy and predictor warps or it does not: profiles/r02b, stall_no_inst).
+template <int T, bool MODE>
+__device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk,
                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
-                                           const LiveCtx &lc) {
-    const bool lc_publish = lc.publish;
+                                           const LiveCtx &lc, bool live) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
     const int32_t order = (int32_t)jb.order;
-    // LIVE (2-channel streams, V): the decoded samples replace the residuals in the ring slot and the emit warp takes
-    // them from there; otherwise they are parked in the scratch.
     const bool fir_order = order == 4 || order == 5 || order == 6 || order == 8;
     const uint32_t fir_from = fir_order ? (uint32_t)order + 1u : 0xffffffffu;
     const bool copy = order == 0;  // order 0 copies; warm-up and order 31 accumulate
@@ -1443,7 +1335,6 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 #pragma unroll
     for (int t = 0; t <= T; t++) h[t] = 0;
     int32_t dprev = 0;
-    int32_t *outp = dst;
     const uint32_t nchunks = max(1u, (jb.nmax + CHUNK - 1) / CHUNK);
     // From the second ring slot on every FIR lane is past its warm-up (order <= 8 < 32). If the warp carries nothing but
     // such lanes, with samples of at most 31 bits (so a history difference never is INT_MIN) and no pre-pass, the
@@ -1458,16 +1349,17 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
     const uint32_t den_mask = (1u << den) - 1u;
 #pragma unroll 1
     for (uint32_t ck = 0; ck < nchunks; ck++) {
-        const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        const uint32_t slot = seq % RING_SLOTS;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
-            wait_full(sm, cons, seq);
+            wait_full(sm, seq);
             rt.add(1, tw);
         }
-        const int32_t *src = &sm.ring[cons][slot][0][lane];
-        int32_t *vdst = &sm.ring[cons][slot][0][lane];
+        const int32_t *src = &sm.ring[slot][0][lane];
+        int32_t *vdst = &sm.ring[slot][0][lane];
+        uint32_t rel0 = 0;
+        if (live) live_prefetch(sm, lane, lc, pk, ck, lc.live_lane, lc.n_lane, lc.sb, lc.shift_bitpos, rel0);  // lands while the slot is predicted
         if (steady_ok && ck > 0) {
-            int32_t *const out_end = dst + (size_t)n_lane * 32u;
 #pragma unroll 2
             for (uint32_t j = 0; j < CHUNK; j++) {
                 const uint32_t code = (uint32_t)src[j * 32];
@@ -1503,9 +1395,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 #pragma unroll
                 for (int t = T; t > 0; t--) h[t] = h[t - 1];
                 h[0] = x;
-                if (LIVE) vdst[j * 32] = x;
-                else if (outp < out_end) *outp = x;
-                outp += 32;
+                vdst[j * 32] = x;
             }
         } else {
 // unroll 2, not more: the entropy warps sharing the SM pay for every extra KB of hot code in instruction fetch
@@ -1554,23 +1444,28 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, int con
 #pragma unroll
             for (int t = T; t > 0; t--) h[t] = h[t - 1];
             h[0] = x;
-            if (LIVE) vdst[j * 32] = x;
-            else if (i < n_lane) *outp = x;
-            outp += 32;
+            vdst[j * 32] = x;
         }
         }
-        if (cons == 1) arrive_vdone(sm, seq);
-        arrive_empty(sm, cons, seq);
+        if (live) {
+            live_chunk_emit(sm, lane, lc, ck, rel0, vdst);
+        } else {  // park the lane's column of the slot: [sample][lane], one 128-byte line per warp store
+            const uint32_t base_i = ck * CHUNK;
+            const uint32_t cnt = n_lane > base_i ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
+            int32_t *outp = dst + (size_t)base_i * 32u;
+#pragma unroll 8
+            for (uint32_t j = 0; j < CHUNK; j++)
+                if (j < cnt) outp[j * 32u] = vdst[j * 32];
+        }
+        arrive_empty(sm, seq);
         seq++;
-        if (lc_publish && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
 }
 
 // Any mix of orders in the warp, including the int16-wrapping ones: unpcBlockGeneral, predictor.go:623-684,
 // with per-lane coefficient width (int32 kept for 4/5/6/8 as the reference's specialised loops do).
-__device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk,
-                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
-                                            bool lc_publish) {
+__device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk,
+                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
@@ -1588,13 +1483,13 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
     const uint32_t nchunks = max(1u, (jb.nmax + CHUNK - 1) / CHUNK);
 #pragma unroll 1
     for (uint32_t ck = 0; ck < nchunks; ck++) {
-        const uint32_t slot = seq % RING_SLOTS, par = (seq / RING_SLOTS) & 1u;
+        const uint32_t slot = seq % RING_SLOTS;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
-            wait_full(sm, cons, seq);
+            wait_full(sm, seq);
             rt.add(1, tw);
         }
-        const int32_t *src = &sm.ring[cons][slot][0][lane];
+        const int32_t *src = &sm.ring[slot][0][lane];
 #pragma unroll 1
         for (uint32_t j = 0; j < CHUNK; j++) {
             const uint32_t i = ck * CHUNK + j;
@@ -1629,70 +1524,58 @@ __device__ __noinline__ void stream_generic(DecShared &sm, uint32_t lane, int co
                 dst[(size_t)i * 32u] = x;
             }
         }
-        if (cons == 1) arrive_vdone(sm, seq);
-        arrive_empty(sm, cons, seq);
+        arrive_empty(sm, seq);
         seq++;
-        if (lc_publish && ((seq & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq);  // every 4th slot and the last one
     }
 }
 
-// The two halves of an interleaved escape pair (decoder.go:513-533) arrive on both rings in lock step; the raw samples
-// are only parked (order 0, no pre-pass), slot by slot, ring 0 then ring 1. The first ring-0 slot is already full.
-__device__ __forceinline__ void stream_escape_pair(DecShared &sm, uint32_t lane, uint32_t *seq, const Job &j0, bool act0,
+// The two halves of an interleaved escape pair (decoder.go:513-533) arrive in alternating ring slots; the raw samples are
+// only parked (order 0, no pre-pass). The first slot (first half, chunk 0) is already full.
+__device__ __forceinline__ void stream_escape_pair(DecShared &sm, uint32_t lane, uint32_t &seq, const Job &j0, bool act0,
                                                    int32_t *__restrict__ dst0, bool valid, const DevConfig &cfg,
-                                                   int32_t *__restrict__ scratch_lane, bool publish, RoleTimer &rt) {
+                                                   int32_t *__restrict__ scratch_lane, RoleTimer &rt) {
     const uint32_t nchunks = max(1u, (j0.nmax + CHUNK - 1) / CHUNK);
+    const uint32_t n0 = act0 ? j0.n : 0u;
     uint32_t n1 = 0;
     int32_t *dst1 = scratch_lane;
 #pragma unroll 1
     for (uint32_t ck = 0; ck < nchunks; ck++) {
-        {
-            const uint32_t slot = seq[0] % RING_SLOTS, par = (seq[0] / RING_SLOTS) & 1u;
-            if (ck > 0) wait_full(sm, 0, seq[0]);
-            const int32_t *src = &sm.ring[0][slot][0][lane];
-            const uint32_t n0 = act0 ? j0.n : 0u;
-#pragma unroll 4
-            for (uint32_t j = 0; j < CHUNK; j++) {
-                const uint32_t i = ck * CHUNK + j;
-                if (i < n0) dst0[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
+#pragma unroll 1
+        for (uint32_t half = 0; half < 2; half++) {
+            const uint32_t slot = seq % RING_SLOTS;
+            if (ck > 0 || half > 0) {
+                const unsigned long long tw = rt.now();
+                wait_full(sm, seq);
+                rt.add(1, tw);
             }
-            arrive_empty(sm, 0, seq[0]);
-            seq[0]++;
-            if (publish && ((seq[0] & 3u) == 0u || ck + 1u == nchunks)) publish_parked(sm, lane, seq[0]);
-        }
-        {
-            const uint32_t slot = seq[1] % RING_SLOTS, par = (seq[1] / RING_SLOTS) & 1u;
-            const unsigned long long tw = rt.now();
-            wait_full(sm, 1, seq[1]);
-            rt.add(1, tw);
-            if (ck == 0) {  // the job of the pair's second half
-                const uint32_t meta = sm.job[1][slot][1][lane];
+            if (ck == 0 && half == 1) {  // the job of the pair's second half
+                const uint32_t meta = sm.job[slot][1][lane];
                 const bool act1 = valid && (meta & 3u) != JOB_INACTIVE;
-                n1 = act1 ? sm.job[1][slot][0][lane] : 0u;
+                n1 = act1 ? sm.job[slot][0][lane] : 0u;
                 dst1 = scratch_lane + (size_t)((meta >> 18) & 7u) * cfg.frame_length * 32u;
             }
-            const int32_t *src = &sm.ring[1][slot][0][lane];
+            const int32_t *src = &sm.ring[slot][0][lane];
+            const uint32_t nn = half ? n1 : n0;
+            int32_t *dd = half ? dst1 : dst0;
 #pragma unroll 4
             for (uint32_t j = 0; j < CHUNK; j++) {
                 const uint32_t i = ck * CHUNK + j;
-                if (i < n1) dst1[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
+                if (i < nn) dd[(size_t)i * 32u] = code_to_residual((uint32_t)src[j * 32]);
             }
-            arrive_vdone(sm, seq[1]);
-            arrive_empty(sm, 1, seq[1]);
-            seq[1]++;
+            arrive_empty(sm, seq);
+            seq++;
         }
     }
 }
 
-// The first slot of the next stream on ring `cons` is full: read its job. Returns the meta word.
-__device__ __forceinline__ uint32_t read_job(DecShared &sm, int cons, uint32_t slot, uint32_t lane, Job &jb) {
-    jb.n = sm.job[cons][slot][0][lane];
-    const uint32_t meta = sm.job[cons][slot][1][lane];
-    jb.coef_bitpos = sm.job[cons][slot][2][lane];
-    jb.nmax = __shfl_sync(FULL_MASK, sm.job[cons][slot][3][lane], 0);
-    jb.live = sm.job[cons][slot][4][lane];
-    jb.shift_bitpos = sm.job[cons][slot][5][lane];
-    jb.u_first_slot = sm.job[cons][slot][6][lane];
+// The first slot of the next stream is full: read its job. Returns the meta word.
+__device__ __forceinline__ uint32_t read_job(DecShared &sm, uint32_t slot, uint32_t lane, Job &jb) {
+    jb.n = sm.job[slot][0][lane];
+    const uint32_t meta = sm.job[slot][1][lane];
+    jb.coef_bitpos = sm.job[slot][2][lane];
+    jb.nmax = __shfl_sync(FULL_MASK, sm.job[slot][3][lane], 0);
+    jb.live = sm.job[slot][4][lane];
+    jb.shift_bitpos = sm.job[slot][5][lane];
     jb.kind = meta & 3u;
     jb.order = (meta >> 2) & 31u;
     jb.den = (meta >> 7) & 15u;
@@ -1702,37 +1585,43 @@ __device__ __forceinline__ uint32_t read_job(DecShared &sm, int cons, uint32_t s
     return meta;
 }
 
-// One stream of ring `cons`, by the loop that fits the orders / modes the warp's lanes carry.
-__device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, int cons, uint32_t &seq, const Packet &pk, const Job &jb,
-                                           bool active, int32_t *__restrict__ dst, RoleTimer &rt, const LiveCtx &lc) {
+// One stream, by the loop that fits the orders / modes the warp's lanes carry.
+__device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk, const Job &jb,
+                                           bool active, int32_t *__restrict__ dst, RoleTimer &rt, LiveCtx &lc,
+                                           const DevConfig &cfg) {
     const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
     const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
     const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
-    // live emission (2-channel streams, ring 1): decided per stream by the entropy warp, uniform over the warp
-    const bool live = cons == 1 && lc.enabled && __any_sync(FULL_MASK, active && (jb.live >> 31) != 0u);
-    if (any_generic) stream_generic(sm, lane, cons, seq, pk, jb, active, dst, rt, lc.publish);
+    // live emission (2-channel streams, V): decided per stream by the entropy warp, uniform over the warp (it only
+    // marks pairs whose orders the register loops take, so a live stream never goes to stream_generic)
+    lc.live_lane = active && (jb.live >> 31) != 0u;
+    const bool live = lc.enabled && !any_generic && __any_sync(FULL_MASK, lc.live_lane);
+    if (live) {
+        lc.n_lane = lc.live_lane ? jb.n : 0u;
+        lc.live_word = jb.live;
+        lc.sb = (cfg.bit_depth == 24 || cfg.bit_depth == 32) ? ((jb.live >> 16) & 3u) * 8u : 0u;
+        lc.shift_bitpos = jb.shift_bitpos;
+        // the U samples of this pair were parked by this warp's own lanes: order them before the cooperative fetches
+        __threadfence_block();
+        __syncwarp();
+    }
+    if (any_generic) stream_generic(sm, lane, seq, pk, jb, active, dst, rt);
     else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
-        if (live) {
-            if (any8) stream_reg<8, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-            else stream_reg<6, true, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        } else if (any8) stream_reg<8, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        else stream_reg<6, true, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-    } else if (live) {
-        if (any8) stream_reg<8, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-        else stream_reg<6, false, true>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-    } else if (any8) stream_reg<8, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
-    else stream_reg<6, false, false>(sm, lane, cons, seq, pk, jb, active, dst, rt, lc);
+        if (any8) stream_reg<8, true>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
+        else stream_reg<6, true>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
+    } else if (any8) stream_reg<8, false>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
+    else stream_reg<6, false>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
+    if (live && lc.live_lane)
+        lc.desc->pad_ = max(1u, (jb.nmax + CHUNK - 1) / CHUNK) * CHUNK;  // frames written so far (zeros past the sample count)
 }
 
-// PREDICTOR warp, one group of 32 packets. The streams of a packet follow each other in the bitstream, so the entropy
-// warp produces them one at a time and one predictor warp serves both rings: ring 0 brings the mono / U stream of every
-// element (and the end of the group), its job says whether a V stream follows on ring 1 or whether ring 1 carries the
-// other half of an interleaved escape pair. `seq` lives across the groups of the CTA.
+// PREDICTOR warp, one group of 32 packets: every stream the entropy warp produces, in order, until the group's end
+// marker. `seq` lives across the groups of the CTA.
 __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
                                                const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
                                                uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch,
                                                PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out,
-                                               uint64_t out_stride, uint32_t group, uint32_t *seq) {
+                                               uint64_t out_stride, uint32_t group, uint32_t &seq) {
     const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
@@ -1747,45 +1636,27 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, con
     lc.bit_depth = cfg.bit_depth;
     lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
     lc.enabled = cfg.num_channels == 2u;
+    lc.live_lane = false;
+    lc.n_lane = lc.live_word = lc.sb = lc.shift_bitpos = 0;
     RoleTimer rt(lane, 3);
     const unsigned long long t_start = rt.now();
 #pragma unroll 1
     for (;;) {
-        const uint32_t slot = seq[0] % RING_SLOTS, par = (seq[0] / RING_SLOTS) & 1u;
+        const uint32_t slot = seq % RING_SLOTS;
         const unsigned long long tw = rt.now();
-        wait_full(sm, 0, seq[0]);
+        wait_full(sm, seq);
         rt.add(1, tw);
         Job jb;
-        const uint32_t meta = read_job(sm, 0, slot, lane, jb);
+        const uint32_t meta = read_job(sm, slot, lane, jb);
         if (jb.kind == JOB_EXIT) {  // written for every lane: the group is finished
-            arrive_empty(sm, 0, seq[0]);
-            seq[0]++;
-            wait_full(sm, 1, seq[1]);  // ring 1's end marker: pass it on to the emit warp
-            arrive_vdone(sm, seq[1]);
-            arrive_empty(sm, 1, seq[1]);
-            seq[1]++;
+            arrive_empty(sm, seq);
+            seq++;
             break;
         }
         const bool active = valid && jb.kind != JOB_INACTIVE;
         int32_t *dst = scratch_lane + (size_t)jb.slot * cfg.frame_length * 32u;
-        lc.publish = cfg.num_channels == 2u;
-        if (meta & JOBF_PAIR) {
-            stream_escape_pair(sm, lane, seq, jb, active, dst, valid, cfg, scratch_lane, lc.publish, rt);
-            continue;
-        }
-        run_stream(sm, lane, 0, seq[0], pk, jb, active, dst, rt, lc);
-        if (meta & JOBF_V_FOLLOWS) {
-            const uint32_t slot1 = seq[1] % RING_SLOTS;
-            const unsigned long long tw1 = rt.now();
-            wait_full(sm, 1, seq[1]);
-            rt.add(1, tw1);
-            Job jv;
-            (void)read_job(sm, 1, slot1, lane, jv);
-            const bool active_v = valid && jv.kind != JOB_INACTIVE;
-            int32_t *dst_v = scratch_lane + (size_t)jv.slot * cfg.frame_length * 32u;
-            lc.publish = false;
-            run_stream(sm, lane, 1, seq[1], pk, jv, active_v, dst_v, rt, lc);
-        }
+        if (meta & JOBF_PAIR) stream_escape_pair(sm, lane, seq, jb, active, dst, valid, cfg, scratch_lane, rt);
+        else run_stream(sm, lane, seq, pk, jb, active, dst, rt, lc, cfg);
     }
     rt.add(0, t_start);
     rt.flush(3);
@@ -2367,8 +2238,8 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
     }
 }
 
-// decodePacketInto (decoder.go:133-207) for groups of 32 packets: persistent CTAs pull group after group from
-// counters[0]; per group the role warps run stages 1+2 (and stage 3 of live pairs), then the whole CTA emits what is left.
+// decodePacketInto (decoder.go:133-207) for groups of 32 packets: persistent two-warp CTAs pull group after group from
+// counters[0]; per group the two role warps run stages 1+2 (and stage 3 of live pairs), then both emit what is left.
 // scratch / descs hold one slot per CTA (gridDim.x), not per group. counters = {next group, CTAs done}: both zero at
 // launch, and the last CTA to leave zeroes them again for the next launch on the same stream.
 __global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
@@ -2385,23 +2256,19 @@ __global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw_warp));
     if (threadIdx.x == 0) {
 #ifndef ALACB200_NAMED_BARRIERS
-        for (int c = 0; c < 2; c++)
-            for (int s = 0; s < RING_SLOTS; s++) {
-                mbar_init(&sm.full_bar[c][s], 32);
-                mbar_init(&sm.empty_bar[c][s], c == 1 ? 64 : 32);
-            }
-        for (int s = 0; s < RING_SLOTS; s++) mbar_init(&sm.vdone_bar[s], 32);
+        for (int s = 0; s < RING_SLOTS; s++) {
+            mbar_init(&sm.full_bar[s], 32);
+            mbar_init(&sm.empty_bar[s], 32);
+        }
 #endif
-        sm.u_chunks_done = 0;
         sm.group = atomicAdd(&counters[0], 1u);
     }
     if (lane == 0) sm.warp_smsp[warp] = hw_warp & 3u;  // %warpid is a hint, but any assignment of roles is correct
     __syncthreads();
     if (threadIdx.x == 0) {
-        // The hardware spreads the warps of a CTA over the SM's sub-partitions, and the entropy warp is the one that must
-        // not share a scheduler with another entropy warp. Per SM, a packed word counts the resident entropy warps of
-        // every sub-partition; the CTA gives the role to its warp on the least loaded one, the predictor and emit roles
-        // to the following warps.
+        // The entropy warp is the one that should not share a scheduler with other entropy warps (it has the least
+        // instruction-level parallelism). Per SM, a packed word counts the resident entropy warps of every
+        // sub-partition; the CTA gives the role to its warp on the less loaded one.
         unsigned int *word = &g_sm_entropy_load[smid & 255u];
         const uint32_t first = atomicAdd(&g_sm_ticket[smid & 255u], 1u) % DEC_WARPS;  // rotates the tie-break
         unsigned int seen = *reinterpret_cast<volatile unsigned int *>(word), assumed;
@@ -2432,14 +2299,12 @@ __global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
     // the CTA's own slot of parked samples and element lists
     int32_t *scratch_cta = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u;
     PacketDesc *descs_cta = descs + (size_t)blockIdx.x * 32u;
-    uint32_t seq[2] = {0, 0};  // ring sequence numbers of this warp's role (the emit warp uses seq[1])
-    uint32_t u_seen = 0;       // emit warp: ring-0 slots known to be parked
+    uint32_t seq = 0;  // ring sequence number of this warp's role
     uint32_t group = sm.group;
 #pragma unroll 1
     while (group < ngroups) {
         if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs_cta, out_bytes, status, group, seq, counters);
-        else if (role == 1) predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq);
-        else if (role == 2) emit_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq[1], u_seen);
+        else predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq);
         __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
         // stage 3 of whatever was not emitted live reuses the window / ring / job memory as its transpose tiles
         EmitArgs ea{packed, offsets, sizes, npackets, scratch_cta, descs_cta, pcm_out, out_stride};

@@ -13,8 +13,8 @@ def line_of(pat):
         if re.search(pat, l): return i
     raise KeyError(pat)
 marks = [(line_of(r'^struct Entropy \{'), 'E.slow'), (line_of(r'^template <bool QUIET>'), 'E.batch'), (line_of(r'void produce_stream\('), 'E.stream'),
-         (line_of(r'^struct ElemHdr'), 'E.parse'), (line_of(r'^__device__ __forceinline__ int32_t delta_step'), 'EMIT'),
-         (line_of(r'void publish_parked\('), 'P.reg'), (line_of(r'__noinline__ void stream_generic'), 'P.generic'),
+         (line_of(r'^struct ElemHdr'), 'E.parse'), (line_of(r'^__device__ __forceinline__ int32_t delta_step'), 'P.emit'),
+         (line_of(r'int32_t sext_bits\('), 'P.reg'), (line_of(r'__noinline__ void stream_generic'), 'P.generic'),
          (line_of(r'void stream_escape_pair\('), 'P.warp'), (line_of(r'^struct EmitArgs'), 'TAIL'), (line_of(r'^__global__ void'), 'KERNEL')]
 def role_of_line(l):
     if l is None or l < marks[0][0]: return None

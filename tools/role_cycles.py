@@ -13,7 +13,7 @@ stride = (dec.frame_bytes + 15) // 16 * 16
 d_packed = torch.from_numpy(wl['packed']).cuda(); d_off = torch.from_numpy(wl['offsets'].view(np.int64)).cuda()
 d_sz = torch.from_numpy(wl['sizes'].view(np.int32)).cuda(); d_pcm = torch.empty(n * stride, dtype=torch.uint8, device='cuda')
 d_nb = torch.zeros(n, dtype=torch.int32, device='cuda'); d_st = torch.zeros(n, dtype=torch.int32, device='cuda')
-nct = min((n + 31) // 32, 148 * 5)
+nct = min((n + 31) // 32, 148 * 8)
 buf = torch.zeros(nct * 16, dtype=torch.int64, device='cuda')
 import os
 if os.environ.get('ALAC_DEBUG_FLAGS'):
@@ -28,7 +28,7 @@ assert f(buf.data_ptr()) == 0
 run(); run()
 f(None)
 b = buf.cpu().numpy().reshape(nct, 16).astype(np.float64)
-names = ['E total', 'E wait-empty', 'E top-up', 'P total', 'P wait-full', '-', '-', '-', 'tail w0', 'tail w1', 'tail w2', 'tag', 'EMIT total', 'EMIT wait']
+names = ['E total', 'E wait-empty', 'E top-up', 'P total', 'P wait-full', '-', '-', '-', 'tail w0', 'tail w1', '-', 'tag', '-', '-']
 for k, nm in enumerate(names):
     if nm in ('tag', '-'): continue
     print(f'{nm:14s} mean {b[:,k].mean()/1e6:8.3f} Mcyc   max {b[:,k].max()/1e6:8.3f} Mcyc')
@@ -39,8 +39,8 @@ per_sm = collections.defaultdict(list)
 for c in range(nct): per_sm[int(smid[c])].append((int(wid[c]), b[c,0]/1e6, (b[c,0]-b[c,1])/1e6))
 raw = buf.cpu().numpy().reshape(nct, 16)
 w14 = raw[:, 14].copy().view(np.uint8).reshape(nct, 8)
-NW = 3
-print('hardware warp slots of CTA warps 0..2 (first 12 CTAs) + entropy SMSP:', [tuple(int(x) for x in w14[c, :5]) for c in range(12)])
+NW = 2
+print('hardware warp slots of CTA warps 0..1 (first 12 CTAs) + entropy SMSP:', [tuple(int(x) for x in w14[c, :5]) for c in range(12)])
 print('CTAs whose warps sit on distinct SMSPs:', int(sum(len(set(int(x) % 4 for x in w14[c, :NW])) == NW for c in range(nct))), 'of', nct)
 print('SMSP histogram of all role warps:', collections.Counter(int(x) % 4 for c in range(nct) for x in w14[c, :NW]))
 print('SMSP histogram of entropy warps:', collections.Counter(int(w14[c, 4]) for c in range(nct)))
@@ -57,4 +57,4 @@ spp = wl['frames'] / n
 eb=(b[:,0]-b[:,1])/(2*spp)
 
 print(f'E busy cycles/sample over CTAs: min {eb.min():.0f} p10 {np.percentile(eb,10):.0f} median {np.median(eb):.0f} p90 {np.percentile(eb,90):.0f} p97 {np.percentile(eb,97):.0f} max {eb.max():.0f}')
-print(f'per decoded sample (frames/packet = {spp:.0f}): E busy {(b[:,0]-b[:,1]).mean()/(2*spp):.0f} cyc,  P busy {(b[:,3]-b[:,4]).mean()/(2*spp):.0f} cyc,  EMIT busy {(b[:,12]-b[:,13]).mean()/spp:.0f} cyc per frame')
+print(f'per decoded sample (frames/packet = {spp:.0f}): E busy {(b[:,0]-b[:,1]).mean()/(2*spp):.0f} cyc,  P busy {(b[:,3]-b[:,4]).mean()/(2*spp):.0f} cyc')
