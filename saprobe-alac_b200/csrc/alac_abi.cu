@@ -663,10 +663,33 @@ int32_t alacb200_decode_packets(alacb200_decoder *dec, const uint8_t *packed, ui
     }
     DeviceGuard guard(dec->pipe.device);
     if (!guard.ok) return ALACB200_E_CUDA;
+    // Chunk schedule: small chunks first and last. Nothing can overlap the upload + decode of the first chunk or the
+    // download of the last one, so those are kept short; the chunks in between are as large as the slots allow.
     const uint32_t chunk = chunk_packets(n, out_stride);
+    std::vector<uint32_t> plan;
+    {
+        uint32_t left = n, cur = std::max(512u, (chunk / 8u + 31u) & ~31u);
+        while (left) {
+            const uint32_t m = std::min(left, cur);
+            plan.push_back(m);
+            left -= m;
+            cur = std::min(chunk, cur * 2u);
+        }
+        if (plan.size() > 3 && plan.back() >= 4096u) {  // ramp down: ... X/2, X/4, X/8, X/8
+            uint32_t x = plan.back();
+            plan.pop_back();
+            for (int k = 0; k < 3; k++) {
+                const uint32_t h = ((x / 2u) + 31u) & ~31u;
+                plan.push_back(h);
+                x -= h;
+            }
+            plan.push_back(x);
+        }
+    }
     int32_t rc = ALACB200_OK;
-    for (uint32_t a = 0; a < n && rc == ALACB200_OK; a += chunk) {
-        const uint32_t m = std::min(n - a, chunk);
+    uint32_t a = 0;
+    for (size_t k = 0; k < plan.size() && rc == ALACB200_OK; a += plan[k], k++) {
+        const uint32_t m = plan[k];
         const Segment seg{packed, packed_bytes, offsets + a, sizes + a, m, pcm_out + (size_t)a * out_stride, out_bytes + a, status + a};
         rc = dec->pipe.submit_chunk(dec->shape, out_stride, &seg, 1);
     }

@@ -577,12 +577,20 @@ struct StreamSpec {
 #define ALACB200_EUNROLL 2  // was 4 while four groups shared an SM; with eight, the loop's footprint in the L0 I-cache counts more
 #endif
 constexpr int E_UNROLL = ALACB200_EUNROLL;
+#ifndef ALACB200_PUNROLL
+#define ALACB200_PUNROLL 2
+#endif
+constexpr int P_UNROLL = ALACB200_PUNROLL;
+#ifndef ALACB200_QUNROLL
+#define ALACB200_QUNROLL 2
+#endif
+constexpr int Q_UNROLL = ALACB200_QUNROLL;
 template <bool QUIET>
 __device__ __forceinline__ bool decode_batch(BitReader &br, Entropy &e, uint32_t &bp, uint32_t pk_size, uint32_t lim,
                                              uint32_t a0, uint32_t a_last) {
     bool saw_run = false;
     const uint32_t a_end = a0 + (CHUNK / 2) * 128u;
-#pragma unroll (QUIET ? 2 : E_UNROLL)
+#pragma unroll (QUIET ? Q_UNROLL : E_UNROLL)
     for (uint32_t aj = a0; aj != a_end; aj += 128u) {
         const uint32_t n0 = br.load(br.qo);  // the word after lo
         const uint32_t w = br.window();
@@ -1360,7 +1368,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
         uint32_t rel0 = 0;
         if (live) live_prefetch(sm, lane, lc, pk, ck, lc.live_lane, lc.n_lane, lc.sb, lc.shift_bitpos, rel0);  // lands while the slot is predicted
         if (steady_ok && ck > 0) {
-#pragma unroll 2
+#pragma unroll P_UNROLL
             for (uint32_t j = 0; j < CHUNK; j++) {
                 const uint32_t code = (uint32_t)src[j * 32];
                 const int32_t r = code_to_residual(code);
