@@ -34,7 +34,7 @@ bool cuda_ok(cudaError_t e, const char *what) {
     } while (0)
 
 constexpr int kSlots = 4;                         // pipeline depth of the host-buffer path
-constexpr uint32_t kMaxChunkPackets = 16384;      // packets per pipeline chunk
+constexpr uint32_t kMaxChunkPackets = 4096;       // packets per pipeline chunk (c3 end to end: 93.7 ms at 16384, 90.2 ms at ~3500, PCIe floor 82.4)
 constexpr uint64_t kMaxChunkPcm = 512ull << 20;   // PCM bytes per pipeline chunk
 
 // Stream-ordered device buffer: growing frees and allocates on the owning stream, so nothing in flight loses its
