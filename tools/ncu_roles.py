@@ -6,16 +6,23 @@ lines (inline asm wrappers at the top of the file) inherit the role of the instr
 import collections, csv, io, os, re, subprocess, sys
 rep = sys.argv[1]
 samples = float(sys.argv[2]) if len(sys.argv) > 2 else 0
-src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'saprobe-alac_b200', 'csrc', 'alac_kernels.cuh')
-lines = open(src).read().split('\n')
-def line_of(pat):
-    for i, l in enumerate(lines, 1):
-        if re.search(pat, l): return i
-    raise KeyError(pat)
-marks = [(line_of(r'^struct Entropy \{'), 'E.slow'), (line_of(r'^template <bool QUIET>'), 'E.batch'), (line_of(r'void produce_stream\('), 'E.stream'),
-         (line_of(r'^struct ElemHdr'), 'E.parse'), (line_of(r'^__device__ __forceinline__ int32_t delta_step'), 'P.emit'),
-         (line_of(r'int32_t sext_bits\('), 'P.reg'), (line_of(r'__noinline__ void stream_generic'), 'P.generic'),
-         (line_of(r'void stream_escape_pair\('), 'P.warp'), (line_of(r'^struct EmitArgs'), 'TAIL'), (line_of(r'^__global__ void'), 'KERNEL')]
+# the kernel source as it was when the capture was made travels inside the report (--import-source on)
+emb = list(csv.reader(io.StringIO(subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda'], capture_output=True, text=True).stdout)))
+lines, take = {}, False
+for r in emb:
+    if not r: continue
+    if r[0] == 'File Path' or r[0] == 'File Name': take = r[1].endswith('alac_kernels.cuh'); continue
+    if take and r[0].isdigit(): lines[int(r[0])] = r[1]
+def line_of(*pats):
+    for pat in pats:
+        for i in sorted(lines):
+            if re.search(pat, lines[i]): return i
+    raise KeyError(pats)
+marks = [(line_of(r'^struct Entropy \{'), 'E.slow'), (line_of(r'^template <bool QUIET>', r'decode_batch\('), 'E.batch'), (line_of(r'void produce_stream\('), 'E.stream'),
+         (line_of(r'^struct ElemHdr'), 'E.parse'), (line_of(r'int32_t delta_step'), 'EMIT'),
+         (line_of(r'int32_t sext_bits\(', r'^template <int T, bool MODE'), 'P.reg'), (line_of(r'__noinline__ void stream_generic'), 'P.generic'),
+         (line_of(r'void stream_escape_pair\(', r'void predictor_warp\('), 'P.warp'), (line_of(r'^struct EmitArgs'), 'TAIL'), (line_of(r'^__global__ void'), 'KERNEL')]
+marks.sort()
 def role_of_line(l):
     if l is None or l < marks[0][0]: return None
     r = None
