@@ -581,6 +581,9 @@ constexpr int E_UNROLL = ALACB200_EUNROLL;
 #define ALACB200_PUNROLL 2
 #endif
 constexpr int P_UNROLL = ALACB200_PUNROLL;
+#ifndef ALACB200_FIRSPLIT
+#define ALACB200_FIRSPLIT 0
+#endif
 #ifndef ALACB200_QUNROLL
 #define ALACB200_QUNROLL 2
 #endif
@@ -1298,11 +1301,16 @@ __device__ __noinline__ void live_chunk_emit(DecShared &sm, uint32_t lane, const
     __syncwarp();  // live_u / live_shift are free for the next slot's requests
 }
 
-// sign-extend the low `bits` (1..32) of v: (v << (32 - bits)) >> (32 - bits) in one SGXT
+// sign-extend the low `bits` (1..32) of v: (v << (32 - bits)) >> (32 - bits) in one SGXT (szext; bfe.s32 cost four instructions)
 __device__ __forceinline__ int32_t sext_bits(int32_t v, uint32_t bits) {
     int32_t r;
-    asm("bfe.s32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(bits));
+    asm("szext.clamp.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(bits));
     return r;
+}
+__device__ __forceinline__ int32_t lds32(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 // if (p) c += a * b, as one predicated IMAD
 __device__ __forceinline__ void mad_if(int32_t &c, int32_t a, int32_t b, bool p) {
@@ -1331,13 +1339,13 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
     const bool mode = MODE && jb.mode != 0;
     const uint32_t n_lane = active ? jb.n : 0u;
     const bool sel4 = order == 4, sel5 = order == 5, sel6 = order == 6;
-    int32_t c[T], h[T + 1], wgt[T];
+    int32_t c[T], h[T + 1], nwgt[T];  // nwgt = -(order - t): both ladders ADD weight * term (one IMAD per tap, no negation)
     uint32_t tmask[T];
 #pragma unroll
     for (int t = 0; t < T; t++) {
         const bool in = fir_order && t < order;
         c[t] = (active && in) ? (int32_t)(int16_t)pk_bits(pk, jb.coef_bitpos + 16u * (uint32_t)t, 16) : 0;
-        wgt[t] = in ? order - t : 0;
+        nwgt[t] = in ? t - order : 0;
         tmask[t] = in ? 0xffffffffu : 0u;
     }
 #pragma unroll
@@ -1368,21 +1376,34 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
         uint32_t rel0 = 0;
         if (live) live_prefetch(sm, lane, lc, pk, ck, lc.live_lane, lc.n_lane, lc.sb, lc.shift_bitpos, rel0);  // lands while the slot is predicted
         if (steady_ok && ck > 0) {
+            // the lane's column of the slot by shared address: one add per unrolled body instead of an index rebuilt from
+            // the thread id (which is what the 128-register budget makes of src[j * 32])
+            const uint32_t a_begin = smem_u32(src), a_end = a_begin + CHUNK * 128u;
 #pragma unroll P_UNROLL
-            for (uint32_t j = 0; j < CHUNK; j++) {
-                const uint32_t code = (uint32_t)src[j * 32];
+            for (uint32_t a = a_begin; a != a_end; a += 128u) {
+                const uint32_t code = (uint32_t)lds32(a);
                 const int32_t r = code_to_residual(code);
                 int32_t top;
                 if (T == 8) top = sel4 ? h[4] : sel5 ? h[5] : sel6 ? h[6] : h[8];
                 else top = sel4 ? h[4] : sel5 ? h[5] : h[6];
                 int32_t d[T];
                 int32_t sum = den_half;
+#if ALACB200_FIRSPLIT
+                int32_t sum_b = 0;  // two accumulators: the dependent IMAD chain of the FIR is half as long (wrap-around sums commute)
+#endif
 #pragma unroll
                 for (int t = 0; t < T; t++) {
                     d[t] = top - h[t];
                     if (t >= 4) d[t] &= (int32_t)tmask[t];  // orders start at 4: taps 0..3 always live
+#if ALACB200_FIRSPLIT
+                    if (t & 1) sum_b -= c[t] * d[t];
+                    else
+#endif
                     sum -= c[t] * d[t];
                 }
+#if ALACB200_FIRSPLIT
+                sum += sum_b;
+#endif
                 const int32_t x = sext_bits(r + top + (sum >> den), jb.chan_bits);
                 const int32_t smask = r >> 31;                       // 0 / -1
                 const int32_t nsone = -(smask | 1);                  // -1 for r > 0, +1 for r < 0: coef -= sign(diff) * sign(r)
@@ -1396,15 +1417,16 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
                     mad_if(c[t], sg, nsone, alive);
                     if (t > 0) {
                         const uint32_t q = ((uint32_t)(sg * d[t]) + bias) >> den;  // |diff| < 2^31: no wrap
-                        E -= wgt[t] * (int32_t)q;
+                        E += nwgt[t] * (int32_t)q;
                         alive = alive && (E >= thr);                 // masked taps: q = 0, E unchanged
                     }
                 }
 #pragma unroll
                 for (int t = T; t > 0; t--) h[t] = h[t - 1];
                 h[0] = x;
-                vdst[j * 32] = x;
+                sts32(a, x);
             }
+            asm volatile("" ::: "memory");  // the slot is re-read through vdst below
         } else {
 // unroll 2, not more: the entropy warps sharing the SM pay for every extra KB of hot code in instruction fetch
 #pragma unroll 2
@@ -1445,7 +1467,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
                 if (alive) c[t] -= sgn;
                 if (t > 0) {
                     const int32_t term = (sgn * d[t]) >> den;
-                    D -= wgt[t] * term;
+                    D += nwgt[t] * term;
                     alive = alive && ((D ^ smask) >= thr);  // masked taps: term 0, D still r: stays alive
                 }
             }
@@ -2031,6 +2053,110 @@ __device__ __forceinline__ void emit_rows(const EmitArgs &x, const DevConfig &cf
     }
 }
 
+// ---- stage 3, packed row path: the shapes real multi-channel files have -- canonical packets of full-length elements,
+// 16-bit, or 24-bit with zero or one shifted byte per element, every shift byte inside the packet. Like emit_rows each lane
+// builds FR frames of ITS packet in a private shared-memory row, but one 32-bit word per sample: the element pass is
+// loads (parked samples + five words of shift bytes), un-mix, ONE byte permute per sample for `(x << 8) | shift byte`
+// (matrix.go:132-135, :270-272) and one STS; the flush packs 16 samples into 3 (24-bit) or 2 (16-bit) 128-bit stores with
+// byte permutes. ~10 instructions per sample instead of ~50 (profiles/r02c_c4: the tail was 22 % of the 7.1 workload's
+// instructions and 43 % of its stall samples).
+template <int BPS, int FR, int NWARPS>
+__device__ __forceinline__ void emit_rows_packed(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
+                                                 bool valid, const Packet &pk, const PacketDesc *desc, uint32_t nops,
+                                                 uint32_t max_ops) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t nch = cfg.num_channels;
+    const uint32_t fb = nch * BPS;
+    const uint32_t row_words = (FR * nch) | 1u;  // odd stride: the lanes' rows are conflict-free
+    uint32_t *roww = reinterpret_cast<uint32_t *>(smem) + ((size_t)warp * 32u + lane) * row_words;
+    const uint32_t pidx = group * 32u + lane;
+    const int32_t *sbase = x.scratch + lane;
+    uint8_t *slot = x.pcm_out + (size_t)pidx * x.out_stride;
+    const uint32_t nbatches = cfg.frame_length / FR;
+    const uint32_t ngroups16 = (FR * nch) / 16u;  // 16 samples -> BPS 128-bit stores
+#pragma unroll 1
+    for (uint32_t b = warp; b < nbatches; b += NWARPS) {
+        const uint32_t f0 = b * FR;
+#pragma unroll 1
+        for (uint32_t e = 0; e < max_ops; e++) {
+            if (e < nops) {
+                const OpDesc op = desc->ops[e];
+                const bool stereo = op.kind == 2;
+                const uint32_t width = stereo ? 2u : 1u;
+                const bool merge = BPS == 3 && op.shift != 0;
+                const int32_t *su = sbase + ((size_t)op.slot * cfg.frame_length + f0) * 32u;
+                const int32_t *sv = su + (size_t)cfg.frame_length * 32u;
+                int32_t lu[FR], lv[FR];
+#pragma unroll
+                for (int q = 0; q < FR; q++) lu[q] = __ldcs(su + (size_t)q * 32u);  // parked samples are read exactly once
+#pragma unroll
+                for (int q = 0; q < FR; q++) lv[q] = stereo ? __ldcs(sv + (size_t)q * 32u) : 0;
+                // FR x width shift bytes from bit `first_bit` of the packet: aligned words, big-endian, one funnel shift each
+                constexpr int NS = FR / 2;  // 32-bit windows a stereo element needs (two frames each); a mono one needs FR / 4
+                uint32_t S[NS];
+#pragma unroll
+                for (int k = 0; k < NS; k++) S[k] = 0;
+                if (merge) {
+                    const uint32_t first_bit = op.shift_bitpos + f0 * width * 8u;
+                    const uint8_t *g0 = pk.p + (first_bit >> 3);
+                    const uint32_t *ga = reinterpret_cast<const uint32_t *>(((uintptr_t)g0) & ~(uintptr_t)3);
+                    const uint32_t bo = (uint32_t)(((uintptr_t)g0) & 3u) * 8u + (first_bit & 7u);
+                    uint32_t W[NS + 1];
+#pragma unroll
+                    for (int k = 0; k <= NS; k++) W[k] = (stereo || k <= NS / 2) ? __byte_perm(__ldg(ga + k), 0, 0x0123) : 0u;
+#pragma unroll
+                    for (int k = 0; k < NS; k++) S[k] = __funnelshift_l(W[k + 1], W[k], bo);
+                }
+                const int32_t mix_res = op.mix_res;
+                const uint32_t mix_bits = op.mix_bits;
+                uint32_t *dstw = roww + op.out_chan;
+#pragma unroll
+                for (int q = 0; q < FR; q++) {
+                    int32_t left = lu[q], right = lv[q];
+                    if (stereo) unmix(lu[q], lv[q], mix_res, mix_bits, left, right);
+                    uint32_t xl = (uint32_t)left, xr = (uint32_t)right;
+                    if (BPS == 3) {
+                        // (x << 8) | shift byte: a pair's bytes sit L R L R in its windows, a mono element's four to a window
+                        const uint32_t ws = S[q >> 1], wm = S[q >> 2];
+                        const uint32_t ml = __byte_perm(stereo ? ws : wm, xl, stereo ? ((q & 1) ? 0x6541 : 0x6543) : 0x6540 + (3 - (q & 3)));
+                        const uint32_t mr = __byte_perm(ws, xr, (q & 1) ? 0x6540 : 0x6542);
+                        xl = merge ? ml : xl;
+                        xr = merge ? mr : xr;
+                    }
+                    dstw[q * nch] = xl;
+                    if (stereo) dstw[q * nch + 1u] = xr;
+                }
+            }
+        }
+        // the lane's row -> its packet slot
+        if (valid) {
+            uint4 *dst = reinterpret_cast<uint4 *>(slot + (size_t)f0 * fb);
+#pragma unroll 1
+            for (uint32_t g = 0; g < ngroups16; g++) {
+                uint32_t v[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) v[k] = roww[g * 16u + k];
+                if (BPS == 3) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t w0 = __byte_perm(v[4 * k], v[4 * k + 1], 0x4210);
+                        const uint32_t w1 = __byte_perm(v[4 * k + 1], v[4 * k + 2], 0x5421);
+                        const uint32_t w2 = __byte_perm(v[4 * k + 2], v[4 * k + 3], 0x6542);
+                        v[3 * k] = w0; v[3 * k + 1] = w1; v[3 * k + 2] = w2;  // 3k+2 < 4(k+1): nothing unread is overwritten
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; k++) dst[g * 3u + k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = __byte_perm(v[2 * k], v[2 * k + 1], 0x5410);
+#pragma unroll
+                    for (int k = 0; k < 2; k++) dst[g * 2u + k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                }
+            }
+        }
+    }
+}
+
 // Stage 3 runs warp-local: every warp owns a transpose tile of 32 packet rows x TL frames (+ a staging row for
 // the shift bytes) inside the shared memory the decode stage leaves behind, and walks the tiles w, w+NWARPS, ...
 // of the group on its own -- no block barrier, three tiles in flight per CTA.
@@ -2104,10 +2230,35 @@ __device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &c
             canon = canon && op.n == n_final && (uint32_t)op.out_chan + w <= cfg.num_channels && (chans & m) == 0u;
             chans |= m;
         }
+        bool packed_ok = canon && chans == (1u << cfg.num_channels) - 1u && nops > 0 && n_final == cfg.frame_length;
         canon = !valid || nops == 0 || (canon && chans == (1u << cfg.num_channels) - 1u);
         const uint32_t FR = (fb & 1u) ? 16u : 8u;  // frames per row: FR * fb must be a multiple of 16
         const uint32_t need = NWARPS * 32u * 4u * ((((FR * fb) / 4u) | 1u) + (row_shift_words(FR) | 1u));
         const bool vec_ok = ((((uintptr_t)x.pcm_out) | x.out_stride) & 15u) == 0;
+        // packed row path: 16-bit, or 24-bit with at most one shifted byte per element and every shift byte (plus the
+        // words the aligned window loads touch) inside the packet
+        {
+            const bool depth_ok = (cfg.bps == 3 && cfg.bit_depth == 24) || (cfg.bps == 2 && cfg.bit_depth == 16);
+            if (cfg.bps == 3)
+                for (uint32_t e = 0; e < nops; e++) {
+                    const OpDesc op = desc->ops[e];
+                    const uint32_t w = op.kind == 2 ? 2u : 1u;
+                    packed_ok = packed_ok && (op.shift == 0 || (op.shift == 1 && (op.shift_bitpos >> 3) >= 4u &&
+                                                                (op.shift_bitpos >> 3) + op.n * w + 8u <= pk.size));
+                }
+            const uint32_t FRP = (cfg.num_channels & 1u) ? 16u : 8u;  // FRP * channels samples: a multiple of 16
+            const uint32_t need_p = NWARPS * 32u * 4u * ((FRP * cfg.num_channels) | 1u);
+            if (depth_ok && vec_ok && __all_sync(FULL_MASK, !valid || packed_ok) && cfg.frame_length % FRP == 0 && need_p <= smem_bytes) {
+                if (cfg.bps == 3) {
+                    if (FRP == 8u) emit_rows_packed<3, 8, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, max_ops);
+                    else emit_rows_packed<3, 16, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, max_ops);
+                } else {
+                    if (FRP == 8u) emit_rows_packed<2, 8, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, max_ops);
+                    else emit_rows_packed<2, 16, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, max_ops);
+                }
+                return;
+            }
+        }
         if (__all_sync(FULL_MASK, canon) && vec_ok && cfg.frame_length % FR == 0 && need <= smem_bytes) {
             if (FR == 8u) {
                 if (cfg.bps == 3) emit_rows<3, 8, NWARPS>(x, cfg, group, smem, valid, pk, desc, nops, n_final, max_ops);
