@@ -582,7 +582,7 @@ constexpr int E_UNROLL = ALACB200_EUNROLL;
 #endif
 constexpr int P_UNROLL = ALACB200_PUNROLL;
 #ifndef ALACB200_FIRSPLIT
-#define ALACB200_FIRSPLIT 0
+#define ALACB200_FIRSPLIT 1
 #endif
 #ifndef ALACB200_QUNROLL
 #define ALACB200_QUNROLL 2
@@ -2169,8 +2169,16 @@ __host__ __device__ inline uint32_t emit_tile_frames(uint32_t frame_bytes, uint3
     return tl >= 16u ? (tl & ~15u) : (tl & ~3u);  // keep TL*fb a multiple of 16 where possible (128-bit stores)
 }
 
+#ifndef ALACB200_TAIL_INLINE
+#define ALACB200_TAIL_INLINE 1
+#endif
+#if ALACB200_TAIL_INLINE
+#define ALACB200_TAIL_FN __forceinline__
+#else
+#define ALACB200_TAIL_FN __noinline__
+#endif
 template <int NWARPS>
-__device__ __forceinline__ void emit_group(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
+__device__ ALACB200_TAIL_FN void emit_group(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
                                            uint32_t smem_bytes) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t fb = cfg.num_channels * cfg.bps;  // bytes per frame
