@@ -526,10 +526,12 @@ def api_legs(pkg, wl_c2, wl_c1, steps):
         r = subprocess.run([exe, 'read', f('c1.m4a'), str(max(5, min(steps, 20)))], capture_output=True, text=True, timeout=600)
         if r.returncode == 0:
             dt, nbytes, _, reuse = r.stdout.split()[:4]
+            phases = [float(v) * 1e3 for v in r.stdout.split()[4:7]]
             samples = wl_c1['frames'] * wl_c1['channels']
             assert int(nbytes) == samples * 2
             out['NewDecoder_Read_c1'] = {'value': samples / float(dt), 'unit': 'samples/s', 'ms_per_file': float(dt) * 1e3,
                                          'x_realtime': wl_c1['seconds'] / float(dt), 'ms_per_file_decoder_kept_open': float(reuse) * 1e3,
+                                         'ms_new_firstread_close': phases,
                                          'how': 'alac::Decoder::New + Read in 32 KiB pieces to EOF over the 60 s M4A (BASELINE configs[0]); the file '
                                                 'image is pinned once and read in place, one GPU call per 2048-packet window'}
         else:

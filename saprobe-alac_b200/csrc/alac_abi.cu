@@ -37,6 +37,40 @@ constexpr int kSlots = 4;                         // pipeline depth of the host-
 constexpr uint32_t kMaxChunkPackets = 4096;       // packets per pipeline chunk (c3 end to end: 93.7 ms at 16384, 90.2 ms at ~3500, PCIe floor 82.4)
 constexpr uint64_t kMaxChunkPcm = 512ull << 20;   // PCM bytes per pipeline chunk
 
+// Device memory of every decoder of the process comes from one stream-ordered pool per device that KEEPS what is freed
+// (up to kPoolKeepBytes) instead of handing it back to the driver at the next synchronisation, which is what the
+// device's default pool does: a caller that opens one decoder per file (NewDecoder, decode.go:50-75) would otherwise pay
+// the physical allocation of its staging and scratch -- tens of milliseconds -- for every file.
+constexpr uint64_t kPoolKeepBytes = 8ull << 30;
+cudaMemPool_t device_pool() {  // of the current device; nullptr: use the device's default pool
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    static bool tried[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!tried[dev]) {
+        tried[dev] = true;
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            uint64_t keep = kPoolKeepBytes;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pools[dev] = pool;  // never destroyed: lives as long as the process
+        }
+        cudaGetLastError();
+    }
+    return pools[dev];
+}
+cudaError_t pool_alloc(void **p, size_t bytes, cudaStream_t stream) {
+    cudaMemPool_t pool = device_pool();
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, stream) : cudaMallocAsync(p, bytes, stream);
+}
+
 // Stream-ordered device buffer: growing frees and allocates on the owning stream, so nothing in flight loses its
 // memory and the device is never synchronised. Contents are not preserved.
 struct DevBuf {
@@ -46,7 +80,7 @@ struct DevBuf {
         if (bytes <= cap) return true;
         release(stream);
         const size_t want = bytes + bytes / 8 + 256;
-        if (cudaMallocAsync(&p, want, stream) != cudaSuccess) {
+        if (pool_alloc(&p, want, stream) != cudaSuccess) {
             g_last_error = "cudaMallocAsync failed";
             cudaGetLastError();
             p = nullptr;
@@ -133,7 +167,7 @@ struct Work {
         if (!scratch.reserve((size_t)ctas * per_cta_scratch, stream) || !descs.reserve((size_t)ctas * 32u * sizeof(PacketDesc), stream))
             return false;
         if (!counters) {
-            if (cudaMallocAsync((void **)&counters, 2 * sizeof(uint32_t), stream) != cudaSuccess ||
+            if (pool_alloc((void **)&counters, 2 * sizeof(uint32_t), stream) != cudaSuccess ||
                 cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), stream) != cudaSuccess) {
                 g_last_error = "cudaMallocAsync failed (group counters)";
                 cudaGetLastError();
@@ -235,6 +269,7 @@ struct Pipeline {
     int device = -1;
     uint32_t num_sms = 148;
     uint32_t max_ctas = 0;  // CTAs the device keeps resident (SMs x CTAs per SM): the grid never needs more
+    uint32_t max_ctas_lat = 0;  // the same for the register-rich build that small batches run
     Slot slots[kSlots];
     uint32_t next_slot = 0;
     bool profiling = false;
@@ -246,14 +281,17 @@ struct Pipeline {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         num_sms = (uint32_t)sms;
-        CU(cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
-        int per_sm = 0;  // persistent CTAs: as many as the device keeps resident
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, alac_decode_kernel, DEC_THREADS, sizeof(DecShared)));
-        if (per_sm <= 0) {
+        CU(cudaFuncSetAttribute(alac_decode_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
+        CU(cudaFuncSetAttribute(alac_decode_kernel<CTAS_PER_SM_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
+        int per_sm = 0, per_sm_lat = 0;  // persistent CTAs: as many as the device keeps resident
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, alac_decode_kernel<CTAS_PER_SM>, DEC_THREADS, sizeof(DecShared)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lat, alac_decode_kernel<CTAS_PER_SM_LAT>, DEC_THREADS, sizeof(DecShared)));
+        if (per_sm <= 0 || per_sm_lat <= 0) {
             g_last_error = "alac_decode_kernel does not fit on this device";
             return ALACB200_E_CUDA;
         }
         max_ctas = (uint32_t)(per_sm * sms);
+        max_ctas_lat = (uint32_t)(per_sm_lat * sms);
         if (std::getenv("ALACB200_VERBOSE"))
             std::fprintf(stderr, "alacb200: device %d, %d SMs x %d resident CTAs of %d threads, %zu B shared each\n", dev, sms, per_sm,
                          DEC_THREADS, sizeof(DecShared));
@@ -294,7 +332,9 @@ struct Pipeline {
         // one scratch slot per CTA; very long frames (up to 65536 x 8 channels = 64 MB per slot) get fewer CTAs
         const uint64_t per_cta = (uint64_t)c.num_channels * c.frame_length * 32u * sizeof(int32_t);
         const uint32_t budget_ctas = (uint32_t)std::max<uint64_t>(8, (4ull << 30) / per_cta);
-        const uint32_t grid = std::min(groups, std::min(max_ctas, budget_ctas));
+        // a batch that fits the register-rich build in one wave runs that build
+        const bool lat = groups <= max_ctas_lat && !std::getenv("ALACB200_NO_LAT_BUILD");
+        const uint32_t grid = std::min(groups, std::min(lat ? max_ctas_lat : max_ctas, budget_ctas));
         if (!work.reserve(grid, (size_t)per_cta, stream)) return ALACB200_E_NOMEM;
         ProfEvents pe{};
         if (profiling) {
@@ -302,9 +342,10 @@ struct Pipeline {
             CU(cudaEventCreate(&pe.e1));
             CU(cudaEventRecord(pe.e0, stream));
         }
-        alac_decode_kernel<<<grid, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
-                                                                             (PacketDesc *)work.descs.p, d_pcm, out_stride, d_out_bytes,
-                                                                             d_status, work.counters);
+        auto *kernel = lat ? alac_decode_kernel<CTAS_PER_SM_LAT> : alac_decode_kernel<CTAS_PER_SM>;
+        kernel<<<grid, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
+                                                                 (PacketDesc *)work.descs.p, d_pcm, out_stride, d_out_bytes, d_status,
+                                                                 work.counters);
         CU(cudaGetLastError());
         if (profiling) {
             CU(cudaEventRecord(pe.e1, stream));

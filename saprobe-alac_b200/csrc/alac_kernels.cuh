@@ -248,7 +248,15 @@ struct RoleTimer {
 // ~2.4 of its 4 warps per scheduler busy (issue slots 55 %); with two always-busy warps per group, 64 threads x 128
 // registers and ~27 KB of shared memory, EIGHT groups are resident per SM instead of four.
 constexpr int DEC_THREADS = 64;
-constexpr int CTAS_PER_SM = 8;
+constexpr int CTAS_PER_SM = 8;        // throughput build of the kernel: 128 registers per thread
+// Batches that cannot fill eight CTAs per SM anyway run a second build of the same kernel with the register budget of
+// six (168 registers: the spills of the 128-register build are gone, and with 222 KB of the SM's 228 KB carved out as
+// shared memory a spill reload is an L1 miss): c2 1.72 -> 1.58 ms, c4 10.7 -> 9.8 ms; c3 is the same at either budget,
+// the 93 k-packet batch 5 % slower at six.
+#ifndef ALACB200_CTAS_PER_SM_LAT
+#define ALACB200_CTAS_PER_SM_LAT 6
+#endif
+constexpr int CTAS_PER_SM_LAT = ALACB200_CTAS_PER_SM_LAT;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int RING_SLOTS = 2;    // ring depth
 constexpr int CHUNK = 32;        // samples per ring slot
@@ -266,6 +274,10 @@ struct DecShared {
     // live emission (2-channel streams): the parked U samples and the shift bytes of the current 32-frame chunk
     int32_t live_u[CHUNK][32];
     uint4 live_shift[32][LIVE_SHIFT_CHUNKS + 1];
+    // per lane, of the live pair being emitted: sample count / live word (bit 31: lane is live) | (packet address & 15) << 18 /
+    // bit position of the shift bytes. In shared memory because the predictor loop has no registers to spare for them and
+    // local memory does not stay in L1 behind the streaming stores (profiles/r02g_c2: 17 % of the predictor warp's time)
+    uint32_t live_ctx[3][32];
     // barriers last: stage 3 reuses everything in front of them as its transpose tiles
     uint64_t full_bar[RING_SLOTS];
     uint64_t empty_bar[RING_SLOTS];
@@ -1066,23 +1078,35 @@ __device__ __forceinline__ uint32_t shift_field(const uint32_t *row_words, uint3
     return win >> (32u - sb);
 }
 
-// What the predictor warp needs to emit PCM itself (2-channel streams).
-struct LiveCtx {
-    const int32_t *u_base;  // parked U samples of this group, [sample][lane]
-    uint8_t *slot;          // this lane's packet slot in pcm_out
-    PacketDesc *desc;
-    uint32_t frame_length, bps, bit_depth;
-    bool vec_ok, enabled;
-    // of the V stream being emitted:
-    bool live_lane;         // this lane's pair is emitted live
-    uint32_t n_lane, live_word, sb, shift_bitpos;
+// What the predictor warp needs to emit PCM itself (2-channel streams), apart from the per-lane words in
+// DecShared::live_ctx: launch facts that rematerialise from the kernel's parameter bank. Only ever handed to inlined
+// code, so it never has an address.
+struct LiveEnv {
+    const int32_t *u_base;  // parked U samples of this CTA, [sample][lane]
+    uint8_t *pcm_out;
+    uint64_t out_stride;
+    PacketDesc *desc;       // this lane's descriptor
+    uint32_t frame_length, bps, bit_depth, pidx;
+    bool enabled;
 };
+__device__ __forceinline__ uint32_t live_shift_bits(uint32_t bit_depth, uint32_t live_word) {
+    return (bit_depth == 24 || bit_depth == 32) ? ((live_word >> 16) & 3u) * 8u : 0u;
+}
+// bit offset, inside the staged shift row, of the first shift field of chunk `ck` (the row starts at the 16-byte aligned
+// address at or below the field's byte)
+__device__ __forceinline__ uint32_t live_rel0(uint32_t live_word, uint32_t shift_bitpos, uint32_t sb, uint32_t ck) {
+    const uint32_t first_bit = shift_bitpos + ck * CHUNK * 2u * sb;
+    const uint32_t lead = (((live_word >> 18) & 15u) + (first_bit >> 3)) & 15u;
+    return lead * 8u + (first_bit & 7u);
+}
 
 // Start fetching what the emission of chunk `ck` needs: the parked U samples of the 32 frames (one 4 KB block,
 // cooperative) and this lane's shift bytes, all by cp.async so they land while the predictor runs.
-__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const LiveCtx &lc, const Packet &pk, uint32_t ck,
-                                              bool live_lane, uint32_t n_lane, uint32_t sb, uint32_t shift_bitpos,
-                                              uint32_t &rel0) {
+__device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, const LiveEnv &lc, const Packet &pk, uint32_t ck) {
+    const uint32_t n_lane = sm.live_ctx[0][lane], live_word = sm.live_ctx[1][lane];
+    const uint32_t sb = live_shift_bits(lc.bit_depth, live_word);
+    const uint32_t shift_bitpos = sm.live_ctx[2][lane];
+    const bool live_lane = (live_word >> 31) != 0u;
     const uint32_t base_i = ck * CHUNK;
     const uint8_t *ug = reinterpret_cast<const uint8_t *>(lc.u_base + (size_t)base_i * 32u);
     const uint32_t frames_left = lc.frame_length > base_i ? lc.frame_length - base_i : 0u;
@@ -1095,7 +1119,6 @@ __device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, cons
                      "l"(ug + (nb ? (size_t)piece * 16u : 0)), "r"(nb)
                      : "memory");
     }
-    rel0 = 0;
     const uint32_t cnt = (live_lane && n_lane > base_i) ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
     if (sb && cnt) {
         const uint32_t first_bit = shift_bitpos + base_i * 2u * sb;
@@ -1116,15 +1139,21 @@ __device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, cons
                              : "memory");
             }
         }
-        rel0 = lead * 8u + (first_bit & 7u);
     }
 }
+
+// Where and in which shape a live pair's PCM leaves (built inside live_chunk_emit from by-value arguments).
+struct LiveOut {
+    uint8_t *slot;  // this lane's packet slot in pcm_out
+    uint32_t frame_length, bit_depth;
+    bool vec_ok;
+};
 
 // Generic (any depth / shift) emission of the 32 frames of chunk `ck` of a live pair: V from the ring slot, U from live_u,
 // shift bytes from live_shift; two batches of 16 frames, each leaving as 2*BPS 128-bit stores to the lane's own packet
 // slot (matrix.go:30-215).
 template <int BPS>
-__device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
+__device__ __noinline__ void live_emit_generic(DecShared &sm, uint32_t lane, const LiveOut lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
                                           const int32_t *vsrc) {
     constexpr int FB = 2 * BPS;
@@ -1198,7 +1227,7 @@ __device__ __forceinline__ void unmix(int32_t u, int32_t v, int32_t mix_res, uin
 
 // Store the packed words of FRAMES frames (NW4 x 16 bytes) to the lane's packet slot.
 template <int NW4, int FRAMES>
-__device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint32_t fb, const uint32_t *ow, bool live_lane) {
+__device__ __forceinline__ void store_batch(const LiveOut &lc, uint32_t f0, uint32_t fb, const uint32_t *ow, bool live_lane) {
     if (!live_lane) return;
     uint8_t *dst = lc.slot + (size_t)f0 * fb;
     const uint32_t frames_here = min((uint32_t)FRAMES, lc.frame_length - f0);
@@ -1225,7 +1254,7 @@ __device__ __forceinline__ void store_batch(const LiveCtx &lc, uint32_t f0, uint
 // ring slot between two stretches of the predictor loop, and what it evicts from the instruction cache costs more than
 // the loop overhead.
 template <int BPS>
-__device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, bool live_lane,
+__device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const LiveOut &lc, uint32_t ck, bool live_lane,
                                           uint32_t n_lane, uint32_t live_word, uint32_t sb, uint32_t rel0,
                                           const int32_t *vsrc) {
     const bool fast = (BPS == 2 && lc.bit_depth == 16) || (BPS == 3 && lc.bit_depth == 24 && sb == 8u);
@@ -1291,13 +1320,25 @@ __device__ __forceinline__ void live_emit(DecShared &sm, uint32_t lane, const Li
 // Stage 3 of one ring slot of a live pair, by the predictor warp itself: the slot holds the decoded V samples, live_u /
 // live_shift were requested (live_prefetch) before the slot was predicted. One copy of the packing code for every
 // instantiation of the predictor loop.
-__device__ __noinline__ void live_chunk_emit(DecShared &sm, uint32_t lane, const LiveCtx &lc, uint32_t ck, uint32_t rel0,
-                                             const int32_t *vsrc) {
+// Arguments by value, per-lane stream facts from DecShared::live_ctx: nothing here lives in local memory.
+// `shape` = bytes per sample | bit depth << 8 | (slots 16-byte aligned) << 16.
+__device__ __noinline__ void live_chunk_emit(DecShared &sm, uint32_t lane, uint8_t *slot, uint32_t frame_length, uint32_t shape,
+                                             uint32_t ck, const int32_t *vsrc) {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();  // live_u is fetched cooperatively
-    if (lc.bps == 3) live_emit<3>(sm, lane, lc, ck, lc.live_lane, lc.n_lane, lc.live_word, lc.sb, rel0, vsrc);
-    else if (lc.bps == 2) live_emit<2>(sm, lane, lc, ck, lc.live_lane, lc.n_lane, lc.live_word, lc.sb, rel0, vsrc);
-    else live_emit<4>(sm, lane, lc, ck, lc.live_lane, lc.n_lane, lc.live_word, lc.sb, rel0, vsrc);
+    LiveOut lo;
+    lo.slot = slot;
+    lo.frame_length = frame_length;
+    lo.bit_depth = (shape >> 8) & 0xffu;
+    lo.vec_ok = ((shape >> 16) & 1u) != 0;
+    const uint32_t bps = shape & 0xffu;
+    const uint32_t n_lane = sm.live_ctx[0][lane], live_word = sm.live_ctx[1][lane], shift_bitpos = sm.live_ctx[2][lane];
+    const bool live_lane = (live_word >> 31) != 0u;
+    const uint32_t sb = live_shift_bits(lo.bit_depth, live_word);
+    const uint32_t rel0 = sb ? live_rel0(live_word, shift_bitpos, sb, ck) : 0u;
+    if (bps == 3) live_emit<3>(sm, lane, lo, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+    else if (bps == 2) live_emit<2>(sm, lane, lo, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
+    else live_emit<4>(sm, lane, lo, ck, live_lane, n_lane, live_word, sb, rel0, vsrc);
     __syncwarp();  // live_u / live_shift are free for the next slot's requests
 }
 
@@ -1328,7 +1369,7 @@ __device__ __forceinline__ void mad_if(int32_t &c, int32_t a, int32_t b, bool p)
 template <int T, bool MODE>
 __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk,
                                            const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
-                                           const LiveCtx &lc, bool live) {
+                                           const LiveEnv &lc, bool live) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
@@ -1373,8 +1414,7 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
         }
         const int32_t *src = &sm.ring[slot][0][lane];
         int32_t *vdst = &sm.ring[slot][0][lane];
-        uint32_t rel0 = 0;
-        if (live) live_prefetch(sm, lane, lc, pk, ck, lc.live_lane, lc.n_lane, lc.sb, lc.shift_bitpos, rel0);  // lands while the slot is predicted
+        if (live) live_prefetch(sm, lane, lc, pk, ck);  // lands while the slot is predicted
         if (steady_ok && ck > 0) {
             // the lane's column of the slot by shared address: one add per unrolled body instead of an index rebuilt from
             // the thread id (which is what the 128-register budget makes of src[j * 32])
@@ -1478,7 +1518,9 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
         }
         }
         if (live) {
-            live_chunk_emit(sm, lane, lc, ck, rel0, vdst);
+            const bool vec_ok = ((((uintptr_t)lc.pcm_out) | lc.out_stride) & 15u) == 0;
+            live_chunk_emit(sm, lane, lc.pcm_out + (size_t)lc.pidx * lc.out_stride, lc.frame_length,
+                            lc.bps | (lc.bit_depth << 8) | ((vec_ok ? 1u : 0u) << 16), ck, vdst);
         } else {  // park the lane's column of the slot: [sample][lane], one 128-byte line per warp store
             const uint32_t base_i = ck * CHUNK;
             const uint32_t cnt = n_lane > base_i ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
@@ -1617,20 +1659,19 @@ __device__ __forceinline__ uint32_t read_job(DecShared &sm, uint32_t slot, uint3
 
 // One stream, by the loop that fits the orders / modes the warp's lanes carry.
 __device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk, const Job &jb,
-                                           bool active, int32_t *__restrict__ dst, RoleTimer &rt, LiveCtx &lc,
+                                           bool active, int32_t *__restrict__ dst, RoleTimer &rt, const LiveEnv &lc,
                                            const DevConfig &cfg) {
     const bool any_generic = __any_sync(FULL_MASK, active && jb.kind == JOB_GENERIC);
     const bool any8 = __any_sync(FULL_MASK, active && jb.order == 8);
     const bool any_mode = __any_sync(FULL_MASK, active && jb.mode != 0);
     // live emission (2-channel streams, V): decided per stream by the entropy warp, uniform over the warp (it only
     // marks pairs whose orders the register loops take, so a live stream never goes to stream_generic)
-    lc.live_lane = active && (jb.live >> 31) != 0u;
-    const bool live = lc.enabled && !any_generic && __any_sync(FULL_MASK, lc.live_lane);
+    const bool live_lane = active && (jb.live >> 31) != 0u;
+    const bool live = lc.enabled && !any_generic && __any_sync(FULL_MASK, live_lane);
     if (live) {
-        lc.n_lane = lc.live_lane ? jb.n : 0u;
-        lc.live_word = jb.live;
-        lc.sb = (cfg.bit_depth == 24 || cfg.bit_depth == 32) ? ((jb.live >> 16) & 3u) * 8u : 0u;
-        lc.shift_bitpos = jb.shift_bitpos;
+        sm.live_ctx[0][lane] = live_lane ? jb.n : 0u;
+        sm.live_ctx[1][lane] = live_lane ? (jb.live | ((uint32_t)((uintptr_t)pk.p & 15u) << 18)) : 0u;  // bit 31: this lane is live
+        sm.live_ctx[2][lane] = jb.shift_bitpos;
         // the U samples of this pair were parked by this warp's own lanes: order them before the cooperative fetches
         __threadfence_block();
         __syncwarp();
@@ -1641,7 +1682,7 @@ __device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, uint32_
         else stream_reg<6, true>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
     } else if (any8) stream_reg<8, false>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
     else stream_reg<6, false>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
-    if (live && lc.live_lane)
+    if (live && live_lane)
         lc.desc->pad_ = max(1u, (jb.nmax + CHUNK - 1) / CHUNK) * CHUNK;  // frames written so far (zeros past the sample count)
 }
 
@@ -1657,17 +1698,16 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, con
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     int32_t *scratch_lane = scratch + lane;  // the CTA's own scratch, [slot][sample][lane]
-    LiveCtx lc;
+    LiveEnv lc;
     lc.u_base = scratch;  // slot 0: the U channel of a 2-channel stream
-    lc.slot = pcm_out + (size_t)pidx * out_stride;
+    lc.pcm_out = pcm_out;
+    lc.out_stride = out_stride;
     lc.desc = descs + lane;
     lc.frame_length = cfg.frame_length;
     lc.bps = cfg.bps;
     lc.bit_depth = cfg.bit_depth;
-    lc.vec_ok = ((((uintptr_t)pcm_out) | out_stride) & 15u) == 0;
+    lc.pidx = pidx;
     lc.enabled = cfg.num_channels == 2u;
-    lc.live_lane = false;
-    lc.n_lane = lc.live_word = lc.sb = lc.shift_bitpos = 0;
     RoleTimer rt(lane, 3);
     const unsigned long long t_start = rt.now();
 #pragma unroll 1
@@ -2409,7 +2449,8 @@ __device__ ALACB200_TAIL_FN void emit_group(const EmitArgs &x, const DevConfig &
 // counters[0]; per group the two role warps run stages 1+2 (and stage 3 of live pairs), then both emit what is left.
 // scratch / descs hold one slot per CTA (gridDim.x), not per group. counters = {next group, CTAs done}: both zero at
 // launch, and the last CTA to leave zeroes them again for the next launch on the same stream.
-__global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(
+template <int OCC>
+__global__ void __launch_bounds__(DEC_THREADS, OCC) alac_decode_kernel(
     const uint8_t *__restrict__ packed, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
     uint32_t npackets, DevConfig cfg, int32_t *__restrict__ scratch, PacketDesc *__restrict__ descs,
     uint8_t *__restrict__ pcm_out, uint64_t out_stride, uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status,

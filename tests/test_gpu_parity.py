@@ -123,10 +123,15 @@ def test_wide_ffmpeg_matrix_gpu(pkg):
     assert npk > 3000
 
 
-def test_synth_hashes_pin_the_gpu(pkg):
+@pytest.mark.parametrize('build', ['by batch size', 'throughput build only'])
+def test_synth_hashes_pin_the_gpu(pkg, build, monkeypatch):
     """The committed drift pin (tests/golden/synth_hashes.json: status word, byte count and PCM of every synthetic case
-    as recorded from the cross-checked oracle) against the CUDA path directly -- not via today's oracle build."""
+    as recorded from the cross-checked oracle) against the CUDA path directly -- not via today's oracle build.
+    The library carries two builds of the one kernel (register budgets of six and of eight CTAs per SM, chosen by batch
+    size); small batches normally run the first, so the second pass forces them through the other one."""
     import synth_pin
+    if build == 'throughput build only':
+        monkeypatch.setenv('ALACB200_NO_LAT_BUILD', '1')
     pin = synth_pin.load_pin()['cases']
     other_input, bad, n = [], [], 0
     decs = {}

@@ -2,7 +2,8 @@
 // as the Go package) timed end to end, host buffers in and out. Used by bench.py for the `e2e_api` legs.
 //   api_bench packets  cookie.bin packed.bin offsets.u64 sizes.u32 steps   PacketDecoder::DecodePackets, all packets per call
 //   api_bench read     file.m4a steps                                      NewDecoder + Read to EOF in 32 KiB pieces (io.Copy)
-// Prints one line: seconds_per_step pcm_bytes fnv1a32_of_the_pcm [seconds_per_step with one decoder kept open]
+// Prints one line: seconds_per_step pcm_bytes fnv1a32_of_the_pcm [seconds_per_step with one decoder kept open, then the
+// NewDecoder / first Read / close shares of a step]
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -57,20 +58,29 @@ int main(int argc, char **argv) {
             std::vector<uint8_t> buf(32 * 1024);
             size_t bytes = 0;
             uint32_t h = 2166136261u;
-            double total = 0;
+            double total = 0, t_new = 0, t_first = 0, t_close = 0;
             for (int s = -2; s < steps; s++) {  // two warm-up passes
                 const auto t0 = clk::now();
                 auto dec = alac::Decoder::New(file);  // NewDecoder is inside the timed region, like tests/benchmark_test.go:261-286
+                const auto t1 = clk::now();
                 size_t got = 0;
                 uint32_t hh = 2166136261u;
+                auto t2 = t1;
                 for (;;) {
                     const size_t k = dec->Read(buf.data(), buf.size());
+                    if (got == 0) t2 = clk::now();  // the first Read decodes the first window
                     if (k == 0) break;
                     got += k;
                     if (s == steps - 1) hh = fnv(hh, buf.data(), k);
                 }
+                const auto t3 = clk::now();
                 dec.reset();
-                if (s >= 0) total += std::chrono::duration<double>(clk::now() - t0).count();
+                if (s >= 0) {
+                    total += std::chrono::duration<double>(clk::now() - t0).count();
+                    t_new += std::chrono::duration<double>(t1 - t0).count();
+                    t_first += std::chrono::duration<double>(t2 - t1).count();
+                    t_close += std::chrono::duration<double>(clk::now() - t3).count();
+                }
                 bytes = got;
                 h = hh;
             }
@@ -84,7 +94,7 @@ int main(int argc, char **argv) {
                     if (dec->Read(buf.data(), buf.size()) == 0) break;
                 if (s >= 0) reuse += std::chrono::duration<double>(clk::now() - t0).count();
             }
-            std::printf("%.9f %zu %u %.9f\n", total / steps, bytes, h, reuse / steps);
+            std::printf("%.9f %zu %u %.9f %.9f %.9f %.9f\n", total / steps, bytes, h, reuse / steps, t_new / steps, t_first / steps, t_close / steps);
             return 0;
         }
     } catch (const std::exception &e) {
