@@ -281,11 +281,11 @@ struct Pipeline {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         num_sms = (uint32_t)sms;
-        CU(cudaFuncSetAttribute(alac_decode_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
-        CU(cudaFuncSetAttribute(alac_decode_kernel<CTAS_PER_SM_LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
+        CU(cudaFuncSetAttribute(alac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
+        CU(cudaFuncSetAttribute(alac_decode_kernel_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecShared)));
         int per_sm = 0, per_sm_lat = 0;  // persistent CTAs: as many as the device keeps resident
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, alac_decode_kernel<CTAS_PER_SM>, DEC_THREADS, sizeof(DecShared)));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lat, alac_decode_kernel<CTAS_PER_SM_LAT>, DEC_THREADS, sizeof(DecShared)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, alac_decode_kernel, DEC_THREADS, sizeof(DecShared)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lat, alac_decode_kernel_lat, DEC_THREADS, sizeof(DecShared)));
         if (per_sm <= 0 || per_sm_lat <= 0) {
             g_last_error = "alac_decode_kernel does not fit on this device";
             return ALACB200_E_CUDA;
@@ -342,7 +342,7 @@ struct Pipeline {
             CU(cudaEventCreate(&pe.e1));
             CU(cudaEventRecord(pe.e0, stream));
         }
-        auto *kernel = lat ? alac_decode_kernel<CTAS_PER_SM_LAT> : alac_decode_kernel<CTAS_PER_SM>;
+        auto *kernel = lat ? alac_decode_kernel_lat : alac_decode_kernel;
         kernel<<<grid, DEC_THREADS, sizeof(DecShared), stream>>>(d_packed, d_offsets, d_sizes, n, c, (int32_t *)work.scratch.p,
                                                                  (PacketDesc *)work.descs.p, d_pcm, out_stride, d_out_bytes, d_status,
                                                                  work.counters);

@@ -2449,10 +2449,9 @@ __device__ ALACB200_TAIL_FN void emit_group(const EmitArgs &x, const DevConfig &
 // counters[0]; per group the two role warps run stages 1+2 (and stage 3 of live pairs), then both emit what is left.
 // scratch / descs hold one slot per CTA (gridDim.x), not per group. counters = {next group, CTAs done}: both zero at
 // launch, and the last CTA to leave zeroes them again for the next launch on the same stream.
-template <int OCC>
-__global__ void __launch_bounds__(DEC_THREADS, OCC) alac_decode_kernel(
+__device__ __forceinline__ void decode_cta(
     const uint8_t *__restrict__ packed, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
-    uint32_t npackets, DevConfig cfg, int32_t *__restrict__ scratch, PacketDesc *__restrict__ descs,
+    uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch, PacketDesc *__restrict__ descs,
     uint8_t *__restrict__ pcm_out, uint64_t out_stride, uint32_t *__restrict__ out_bytes, int32_t *__restrict__ status,
     uint32_t *__restrict__ counters) {
     extern __shared__ __align__(1024) uint8_t dec_smem[];
@@ -2532,6 +2531,24 @@ __global__ void __launch_bounds__(DEC_THREADS, OCC) alac_decode_kernel(
             counters[1] = 0;
         }
     }
+}
+
+#define ALACB200_KERNEL_PARAMS                                                                                              \
+    const uint8_t *__restrict__ packed, const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,          \
+        uint32_t npackets, DevConfig cfg, int32_t *__restrict__ scratch, PacketDesc *__restrict__ descs,                   \
+        uint8_t *__restrict__ pcm_out, uint64_t out_stride, uint32_t *__restrict__ out_bytes,                              \
+        int32_t *__restrict__ status, uint32_t *__restrict__ counters
+// The throughput build (big batches) ...
+#ifdef ALACB200_TP_MAXNREG
+__global__ void __maxnreg__(ALACB200_TP_MAXNREG) alac_decode_kernel(ALACB200_KERNEL_PARAMS) {
+#else
+__global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM) alac_decode_kernel(ALACB200_KERNEL_PARAMS) {
+#endif
+    decode_cta(packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride, out_bytes, status, counters);
+}
+// ... and the register-rich build for batches of at most one wave of it.
+__global__ void __launch_bounds__(DEC_THREADS, CTAS_PER_SM_LAT) alac_decode_kernel_lat(ALACB200_KERNEL_PARAMS) {
+    decode_cta(packed, offsets, sizes, npackets, cfg, scratch, descs, pcm_out, out_stride, out_bytes, status, counters);
 }
 
 }  // namespace alacb200
