@@ -1,23 +1,23 @@
 // alac_kernels.cuh -- the hand-written sm_100a kernel of the ALAC packet-decode hot path.
 //
-// One kernel, alac_decode_kernel, parallel ACROSS packets (packets are independent, decoder.go:79-87) and across
-// STAGES. One CTA = 32 packets, four role warps with lane = packet:
+// One kernel body, decode_cta (built twice: alac_decode_kernel for big batches, alac_decode_kernel_lat with a larger
+// register budget for batches of at most one wave), parallel ACROSS packets (packets are independent, decoder.go:79-87)
+// and across STAGES. A CTA is persistent, pulls groups of 32 packets from a counter and works on a group with two role
+// warps, lane = packet:
 //
 //   ENTROPY     walks the element grammar of decodePacketInto (decoder.go:133-207) and the adaptive Golomb-Rice
 //               stream (DynDecomp, golomb.go:148-253) in branch-free batches of 16 samples (decode_batch) and hands
-//               the codes through shared-memory rings (mbarrier full/empty pairs) to the predictor warps. Compressed
+//               the codes through a shared-memory ring (mbarrier full/empty pairs) to the predictor warp. Compressed
 //               bytes are staged into shared memory with 128-bit cp.async (zero-fill past the packet end) one
 //               period ahead of their use.
-//   PREDICTOR 0 sign-LMS filter (UnpcBlock, predictor.go:45-684) of the mono / U stream of every element; parks the
-//               decoded samples as int32 in a lane-interleaved scratch ([group][slot][sample][32 lanes]: every warp
-//               store is one 128-byte line).
-//   PREDICTOR 1 the same for the V stream, so the serial entropy chain of a packet overlaps both predictor chains.
-//               For 2-channel streams it writes V back into the ring slot instead of parking it.
-//   EMIT        (2-channel streams) un-mix + shift-merge + interleaved little-endian PCM (WriteStereo*, matrix.go:30-215)
-//               of every finished ring slot, 128-bit stores to the packet's own output slot.
+//   PREDICTOR   sign-LMS filter (UnpcBlock, predictor.go:45-684) of every stream of the group in bitstream order. Mono /
+//               U streams are parked as int32 in a lane-interleaved scratch of the CTA ([slot][sample][32 lanes]: every
+//               warp store is one 128-byte line). For the V stream of a 2-channel pair it emits PCM itself, ring slot
+//               by ring slot: un-mix + shift-merge + interleaved little-endian bytes (WriteStereo*, matrix.go:30-215),
+//               128-bit stores to the packet's own output slot.
 //
-// Whatever is not emitted live (mono, multi-channel, escape pairs, short or failed packets) is written by the whole
-// CTA after the role warps are done, from the parked samples (emit_group: WriteStereo*/WriteMono*, matrix.go:30-301).
+// Whatever is not emitted live (mono, multi-channel, escape pairs, short or failed packets) is written by both warps
+// after the group's barrier, from the parked samples (emit_group: WriteStereo*/WriteMono*, matrix.go:30-301).
 //
 // Integer semantics are the Go reference's: wrap-around int32/uint32, shifts >= 32 give 0 / sign
 // fill (PTX shl/shr clamp exactly like that), int32 coefficients for orders 4/5/6/8 and int16-wrapping
