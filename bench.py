@@ -47,6 +47,7 @@ WORKLOADS = {
     'c2': (24, 2, 96000, 600, '24-bit stereo 96 kHz, 10 min, batched DecodePackets (BASELINE configs[1])'),
     'c3': (24, 2, 192000, 3600, '24-bit stereo 192 kHz with shift buffer (bytesShifted=1), 1 h (BASELINE configs[2])'),
     'c4': (24, 8, 48000, 1800, '7.1 24-bit 48 kHz, 30 min (BASELINE configs[3])'),
+    'c3q': (24, 2, 192000, 900, '24-bit stereo 192 kHz with shift buffer, 15 min: the shard one of four GPUs gets of c3 (developer: wave quantisation)'),
     'lib16': (16, 2, 44100, 48 * 180, '48 x 3 min of 16-bit stereo 44.1 kHz in one call, 93 k packets (throughput regime, one depth)'),
     'lsb': (24, 2, 96000, 120, '24-bit stereo 96 kHz, 2 min of +-2 LSB noise: the quiet-passage regime only (developer stress)'),
     'smoke': (24, 2, 96000, 20, '24-bit stereo 96 kHz, 20 s (quick self-test)'),

@@ -415,6 +415,19 @@ struct BitReader {
     }
 };
 
+// Special registers re-read at the point of use (volatile: never hoisted, so nothing derived from them is carried across
+// the hot loops -- or spilled: with 222 of the SM's 228 KB carved out as shared memory a spill reload is an L1 miss).
+__device__ __forceinline__ uint32_t lane_now() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ uint32_t cta_now() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(v));
+    return v;
+}
+
 // The ring carries residuals as the sign-folded codes the entropy stage decodes (golomb.go:207-214: odd -> negative),
 // so the fold is undone by the predictor warps, which have the time.
 __device__ __forceinline__ int32_t code_to_residual(uint32_t nd) { return (int32_t)((nd >> 1) ^ (0u - (nd & 1u))); }
@@ -1082,13 +1095,18 @@ __device__ __forceinline__ uint32_t shift_field(const uint32_t *row_words, uint3
 // DecShared::live_ctx: launch facts that rematerialise from the kernel's parameter bank. Only ever handed to inlined
 // code, so it never has an address.
 struct LiveEnv {
-    const int32_t *u_base;  // parked U samples of this CTA, [sample][lane]
+    const int32_t *scratch;  // the kernel's scratch parameter: CTA b owns [b][channel][sample][lane]
+    uint32_t num_channels;
     uint8_t *pcm_out;
     uint64_t out_stride;
     PacketDesc *desc;       // this lane's descriptor
-    uint32_t frame_length, bps, bit_depth, pidx;
+    uint32_t frame_length, bps, bit_depth;
     bool enabled;
 };
+// this CTA's slot of parked samples, rebuilt from the launch parameters where it is needed
+__device__ __forceinline__ const int32_t *cta_scratch(const LiveEnv &lc) {
+    return lc.scratch + (size_t)cta_now() * lc.num_channels * lc.frame_length * 32u;
+}
 __device__ __forceinline__ uint32_t live_shift_bits(uint32_t bit_depth, uint32_t live_word) {
     return (bit_depth == 24 || bit_depth == 32) ? ((live_word >> 16) & 3u) * 8u : 0u;
 }
@@ -1108,7 +1126,7 @@ __device__ __forceinline__ void live_prefetch(DecShared &sm, uint32_t lane, cons
     const uint32_t shift_bitpos = sm.live_ctx[2][lane];
     const bool live_lane = (live_word >> 31) != 0u;
     const uint32_t base_i = ck * CHUNK;
-    const uint8_t *ug = reinterpret_cast<const uint8_t *>(lc.u_base + (size_t)base_i * 32u);
+    const uint8_t *ug = reinterpret_cast<const uint8_t *>(cta_scratch(lc) + (size_t)base_i * 32u);  // channel 0: U
     const uint32_t frames_left = lc.frame_length > base_i ? lc.frame_length - base_i : 0u;
     const uint32_t ubase = smem_u32(&sm.live_u[0][0]);
 #pragma unroll
@@ -1368,8 +1386,7 @@ __device__ __forceinline__ void mad_if(int32_t &c, int32_t a, int32_t b, bool p)
 // scheduler holds the loops of its entropy and predictor warps or it does not: profiles/r02b, stall_no_inst).
 template <int T, bool MODE>
 __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_t &seq, const Packet &pk,
-                                           const Job &jb, bool active, int32_t *__restrict__ dst, RoleTimer &rt,
-                                           const LiveEnv &lc, bool live) {
+                                           const Job &jb, bool active, RoleTimer &rt, const LiveEnv &lc, bool live) {
     const uint32_t cs = 32u - jb.chan_bits;
     const uint32_t den = jb.den;
     const int32_t den_half = den > 0 ? (int32_t)(1u << (den - 1)) : 0;
@@ -1412,13 +1429,12 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
             wait_full(sm, seq);
             rt.add(1, tw);
         }
-        const int32_t *src = &sm.ring[slot][0][lane];
-        int32_t *vdst = &sm.ring[slot][0][lane];
+        const int32_t *src = &sm.ring[slot][0][lane_now()];
         if (live) live_prefetch(sm, lane, lc, pk, ck);  // lands while the slot is predicted
         if (steady_ok && ck > 0) {
             // the lane's column of the slot by shared address: one add per unrolled body instead of an index rebuilt from
             // the thread id (which is what the 128-register budget makes of src[j * 32])
-            const uint32_t a_begin = smem_u32(src), a_end = a_begin + CHUNK * 128u;
+            const uint32_t a_begin = smem_u32(&sm.ring[slot][0][lane_now()]), a_end = a_begin + CHUNK * 128u;
 #pragma unroll P_UNROLL
             for (uint32_t a = a_begin; a != a_end; a += 128u) {
                 const uint32_t code = (uint32_t)lds32(a);
@@ -1514,17 +1530,22 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
 #pragma unroll
             for (int t = T; t > 0; t--) h[t] = h[t - 1];
             h[0] = x;
-            vdst[j * 32] = x;
+            const_cast<int32_t *>(src)[j * 32] = x;
         }
         }
+        // everything below is rebuilt from the launch parameters and re-read special registers: nothing of it is live
+        // (or spilled) across the sample loop
+        const uint32_t lane_v = lane_now();
+        int32_t *vdst = &sm.ring[slot][0][lane_v];
         if (live) {
             const bool vec_ok = ((((uintptr_t)lc.pcm_out) | lc.out_stride) & 15u) == 0;
-            live_chunk_emit(sm, lane, lc.pcm_out + (size_t)lc.pidx * lc.out_stride, lc.frame_length,
+            const uint32_t pidx = (uint32_t)lds32(smem_u32(&sm.group)) * 32u + lane_v;
+            live_chunk_emit(sm, lane_v, lc.pcm_out + (size_t)pidx * lc.out_stride, lc.frame_length,
                             lc.bps | (lc.bit_depth << 8) | ((vec_ok ? 1u : 0u) << 16), ck, vdst);
         } else {  // park the lane's column of the slot: [sample][lane], one 128-byte line per warp store
             const uint32_t base_i = ck * CHUNK;
             const uint32_t cnt = n_lane > base_i ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
-            int32_t *outp = dst + (size_t)base_i * 32u;
+            int32_t *outp = const_cast<int32_t *>(cta_scratch(lc)) + ((size_t)jb.slot * lc.frame_length + base_i) * 32u + lane_v;
 #pragma unroll 8
             for (uint32_t j = 0; j < CHUNK; j++)
                 if (j < cnt) outp[j * 32u] = vdst[j * 32];
@@ -1678,10 +1699,10 @@ __device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, uint32_
     }
     if (any_generic) stream_generic(sm, lane, seq, pk, jb, active, dst, rt);
     else if (any_mode) {  // rare: the order-31 pre-pass is on for some lane
-        if (any8) stream_reg<8, true>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
-        else stream_reg<6, true>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
-    } else if (any8) stream_reg<8, false>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
-    else stream_reg<6, false>(sm, lane, seq, pk, jb, active, dst, rt, lc, live);
+        if (any8) stream_reg<8, true>(sm, lane, seq, pk, jb, active, rt, lc, live);
+        else stream_reg<6, true>(sm, lane, seq, pk, jb, active, rt, lc, live);
+    } else if (any8) stream_reg<8, false>(sm, lane, seq, pk, jb, active, rt, lc, live);
+    else stream_reg<6, false>(sm, lane, seq, pk, jb, active, rt, lc, live);
     if (live && live_lane)
         lc.desc->pad_ = max(1u, (jb.nmax + CHUNK - 1) / CHUNK) * CHUNK;  // frames written so far (zeros past the sample count)
 }
@@ -1692,21 +1713,22 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, con
                                                const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
                                                uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch,
                                                PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out,
-                                               uint64_t out_stride, uint32_t group, uint32_t &seq) {
+                                               uint64_t out_stride, uint32_t group, uint32_t &seq,
+                                               const int32_t *__restrict__ scratch_all) {
     const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
     int32_t *scratch_lane = scratch + lane;  // the CTA's own scratch, [slot][sample][lane]
     LiveEnv lc;
-    lc.u_base = scratch;  // slot 0: the U channel of a 2-channel stream
+    lc.scratch = scratch_all;  // the kernel parameter; `scratch` is this CTA's part of it
+    lc.num_channels = cfg.num_channels;
     lc.pcm_out = pcm_out;
     lc.out_stride = out_stride;
     lc.desc = descs + lane;
     lc.frame_length = cfg.frame_length;
     lc.bps = cfg.bps;
     lc.bit_depth = cfg.bit_depth;
-    lc.pidx = pidx;
     lc.enabled = cfg.num_channels == 2u;
     RoleTimer rt(lane, 3);
     const unsigned long long t_start = rt.now();
@@ -2511,7 +2533,7 @@ __device__ __forceinline__ void decode_cta(
 #pragma unroll 1
     while (group < ngroups) {
         if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs_cta, out_bytes, status, group, seq, counters);
-        else predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq);
+        else predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq, scratch);
         __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
         // stage 3 of whatever was not emitted live reuses the window / ring / job memory as its transpose tiles
         EmitArgs ea{packed, offsets, sizes, npackets, scratch_cta, descs_cta, pcm_out, out_stride};
@@ -2521,6 +2543,7 @@ __device__ __forceinline__ void decode_cta(
         rt.add(0, t_emit);
         rt.flush(1);
         group = sm.next_group;
+        if (threadIdx.x == 0) sm.group = group;  // the predictor warp re-reads it where it needs the packet index
         __syncthreads();  // the tiles are free again; nobody reads next_group after this point
     }
     if (threadIdx.x == 0) {

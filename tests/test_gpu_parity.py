@@ -238,6 +238,46 @@ def test_strides_and_offsets_for_every_emit_path(pkg):
             dec.close()
 
 
+def test_packed_row_tail_shapes(pkg):
+    """The packed row tail (emit_rows_packed: canonical multi-channel packets of full-length elements, 16-bit, or 24-bit with
+    0 / 1 shifted byte) for every channel count that has elements to interleave, with packets at odd byte offsets (the
+    aligned shift-byte windows then start at every phase), 40 full packets (a whole group and a part of one), slots
+    16-byte aligned and not (the latter must fall back to the byte-granular row path), and a frame length of 1024."""
+    for ch, bits, shift, fl in ((3, 24, 1, 4096), (4, 24, 1, 4096), (5, 16, 0, 4096), (5, 24, 1, 4096), (6, 24, 0, 4096),
+                                (6, 24, 1, 1024), (7, 24, 1, 4096), (8, 16, 0, 4096), (8, 24, 1, 4096), (2, 24, 1, 4096)):
+        ocfg = ol.Config.make(bit_depth=bits, num_channels=ch, sample_rate=48000, frame_length=fl)
+        x = make_signal('silence_lsb', ch, fl * 40, bits, 48000, seed=900 + ch + bits + shift)
+        packets = ol.encode_stream(ocfg, x, ol.PacketOpts.make(bytes_shifted=shift))
+        if ch == 2:  # two mono elements in a 2-channel stream: canonical, not a pair
+            packets = [ol.Writer(ocfg).element(0, x[i * fl:(i + 1) * fl, 0].copy(), order=4, coefs=[60, -30, 10, 5], bytes_shifted=shift)
+                       .element(0, x[i * fl:(i + 1) * fl, 1].copy(), order=5, coefs=[50, -20, 10, 5, 1], bytes_shifted=shift, instance=1)
+                       .end().bytes() for i in range(40)]
+        blob = bytearray(b'\xee' * 3)
+        offs, sizes = [], []
+        for i, p in enumerate(packets):
+            offs.append(len(blob))
+            sizes.append(len(p))
+            blob += p + b'\xdd' * (i % 7)
+        blob += b'\0' * 64
+        packed = np.frombuffer(bytes(blob), dtype=np.uint8)
+        offs = np.array(offs, dtype=np.uint64)
+        sizes = np.array(sizes, dtype=np.uint32)
+        want, want_nb, want_st = ol.decode_batch(ocfg, packed, offs, sizes, nthreads=4)
+        assert (want_st == 0).all() and (want_nb == ocfg.frame_bytes()).all()
+        dec = pkg.NewPacketDecoder(to_pkg_cfg(pkg, ocfg), 0)
+        try:
+            for extra in (0, 16, 4):
+                stride = (dec.frame_bytes + 15) // 16 * 16 + extra
+                canary = np.full((len(packets), stride), 0xA5, dtype=np.uint8)
+                out, nb, st = dec.decode_packed(packed, offs, sizes, out=canary, out_stride=stride)
+                assert np.array_equal(st, want_st) and np.array_equal(nb, want_nb), (ch, bits, shift, extra)
+                assert np.array_equal(out[:, :dec.frame_bytes], want), (ch, bits, shift, extra)
+                gap = out[:, dec.frame_bytes:]
+                assert ((gap == 0) | (gap == 0xA5)).all(), (ch, bits, shift, extra)
+        finally:
+            dec.close()
+
+
 def test_decoder_read_seek_m4a(pkg):
     """NewDecoder/Read/Seek over an M4A (BASELINE configs[0] shape, shortened): conformance_test.go:282-292 (bit-for-bit
     vs source) and :343-421 (seek at 0/25/50/75 % equals the tail of the full decode)."""
