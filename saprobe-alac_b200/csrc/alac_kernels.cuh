@@ -1099,7 +1099,7 @@ struct LiveEnv {
     uint32_t num_channels;
     uint8_t *pcm_out;
     uint64_t out_stride;
-    PacketDesc *desc;       // this lane's descriptor
+    PacketDesc *descs;      // the kernel's descriptor parameter: CTA b owns [b][32]
     uint32_t frame_length, bps, bit_depth;
     bool enabled;
 };
@@ -1421,17 +1421,102 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
     const bool steady_ok = !MODE && __all_sync(FULL_MASK, !active || (fir_order && jb.chan_bits <= 31u));
 #endif
     const uint32_t den_mask = (1u << den) - 1u;
-#pragma unroll 1
-    for (uint32_t ck = 0; ck < nchunks; ck++) {
+    // One ring slot = wait for it, start the fetches its emission needs, run a sample loop over it, emit or park it, hand
+    // it back. Two loops over the slots instead of one with both bodies in it: the general body takes the first slot of
+    // every stream (warm-up) and every slot of a warp the steady body cannot serve, the steady body all others -- so the
+    // invariants of the general body (order, warm-up bounds, pre-pass state) are dead while the steady loop runs and do
+    // not compete with it for the 128 registers.
+    auto slot_begin = [&](uint32_t ck) -> uint32_t {
         const uint32_t slot = seq % RING_SLOTS;
         if (ck > 0) {
             const unsigned long long tw = rt.now();
             wait_full(sm, seq);
             rt.add(1, tw);
         }
-        const int32_t *src = &sm.ring[slot][0][lane_now()];
         if (live) live_prefetch(sm, lane, lc, pk, ck);  // lands while the slot is predicted
-        if (steady_ok && ck > 0) {
+        return slot;
+    };
+    auto slot_end = [&](uint32_t ck, uint32_t slot) {
+        // everything below is rebuilt from the launch parameters and re-read special registers: nothing of it is live
+        // (or spilled) across the sample loop
+        const uint32_t lane_v = lane_now();
+        int32_t *vdst = &sm.ring[slot][0][lane_v];
+        if (live) {
+            const bool vec_ok = ((((uintptr_t)lc.pcm_out) | lc.out_stride) & 15u) == 0;
+            const uint32_t pidx = (uint32_t)lds32(smem_u32(&sm.group)) * 32u + lane_v;
+            live_chunk_emit(sm, lane_v, lc.pcm_out + (size_t)pidx * lc.out_stride, lc.frame_length,
+                            lc.bps | (lc.bit_depth << 8) | ((vec_ok ? 1u : 0u) << 16), ck, vdst);
+        } else {  // park the lane's column of the slot: [sample][lane], one 128-byte line per warp store
+            const uint32_t base_i = ck * CHUNK;
+            const uint32_t cnt = n_lane > base_i ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
+            int32_t *outp = const_cast<int32_t *>(cta_scratch(lc)) + ((size_t)jb.slot * lc.frame_length + base_i) * 32u + lane_v;
+#pragma unroll 8
+            for (uint32_t j = 0; j < CHUNK; j++)
+                if (j < cnt) outp[j * 32u] = vdst[j * 32];
+        }
+        arrive_empty(sm, seq);
+        seq++;
+    };
+    uint32_t ck = 0;
+#pragma unroll 1
+    do {
+        const uint32_t slot = slot_begin(ck);
+        const int32_t *src = &sm.ring[slot][0][lane_now()];
+// unroll 2, not more: the entropy warps sharing the SM pay for every extra KB of hot code in instruction fetch
+#pragma unroll 2
+        for (uint32_t j = 0; j < CHUNK; j++) {
+            const uint32_t i = ck * CHUNK + j;
+            int32_t r = code_to_residual((uint32_t)src[j * 32]);
+            if (MODE) {  // order-31 pre-pass on the residuals (decoder.go:306-308)
+                const int32_t dn = (i == 0) ? r : sext_go(r + dprev, cs);
+                r = mode ? dn : r;
+                dprev = r;
+            }
+            int32_t top;
+            if (T == 8) top = sel4 ? h[4] : sel5 ? h[5] : sel6 ? h[6] : h[8];
+            else top = sel4 ? h[4] : sel5 ? h[5] : h[6];
+            int32_t d[T];
+            int32_t sum = den_half;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                d[t] = top - h[t];
+                if (t >= 4) d[t] &= (int32_t)tmask[t];  // orders start at 4: taps 0..3 always live
+                sum -= c[t] * d[t];
+            }
+            const int32_t fir = sext_go(r + top + (sum >> den), cs);
+            const int32_t warm = (i == 0 || copy) ? r : sext_go(r + h[0], cs);
+            const bool is_fir = i >= fir_from;
+            const int32_t x = is_fir ? fir : warm;
+            // sign-LMS adaptation on the residual's sign: walk the taps from the oldest sample, stop once the
+            // running residual has changed sign or reached zero (predictor.go:137-185)
+            bool alive = is_fir && (r != 0);
+            const int32_t smask = r >> 31;           // 0 / -1
+            const int32_t sone = smask | 1;          // +1 / -1
+            const int32_t thr = 1 + smask;           // continue while (D ^ smask) >= thr <=> D > 0 (r>0) / D < 0 (r<0)
+            int32_t D = r;
+#pragma unroll
+            for (int t = T - 1; t >= 0; t--) {
+                const int32_t sg = max(min(d[t], 1), -1);  // signOfInt
+                const int32_t sgn = sg * sone;             // sign for r > 0, -sign for r < 0
+                if (alive) c[t] -= sgn;
+                if (t > 0) {
+                    const int32_t term = (sgn * d[t]) >> den;
+                    D += nwgt[t] * term;
+                    alive = alive && ((D ^ smask) >= thr);  // masked taps: term 0, D still r: stays alive
+                }
+            }
+#pragma unroll
+            for (int t = T; t > 0; t--) h[t] = h[t - 1];
+            h[0] = x;
+            const_cast<int32_t *>(src)[j * 32] = x;
+        }
+        slot_end(ck, slot);
+        ck++;
+    } while (ck < nchunks && !steady_ok);
+#pragma unroll 1
+    for (; ck < nchunks; ck++) {
+        const uint32_t slot = slot_begin(ck);
+        {
             // the lane's column of the slot by shared address: one add per unrolled body instead of an index rebuilt from
             // the thread id (which is what the 128-register budget makes of src[j * 32])
             const uint32_t a_begin = smem_u32(&sm.ring[slot][0][lane_now()]), a_end = a_begin + CHUNK * 128u;
@@ -1483,75 +1568,8 @@ __device__ __forceinline__ void stream_reg(DecShared &sm, uint32_t lane, uint32_
                 sts32(a, x);
             }
             asm volatile("" ::: "memory");  // the slot is re-read through vdst below
-        } else {
-// unroll 2, not more: the entropy warps sharing the SM pay for every extra KB of hot code in instruction fetch
-#pragma unroll 2
-        for (uint32_t j = 0; j < CHUNK; j++) {
-            const uint32_t i = ck * CHUNK + j;
-            int32_t r = code_to_residual((uint32_t)src[j * 32]);
-            if (MODE) {  // order-31 pre-pass on the residuals (decoder.go:306-308)
-                const int32_t dn = (i == 0) ? r : sext_go(r + dprev, cs);
-                r = mode ? dn : r;
-                dprev = r;
-            }
-            int32_t top;
-            if (T == 8) top = sel4 ? h[4] : sel5 ? h[5] : sel6 ? h[6] : h[8];
-            else top = sel4 ? h[4] : sel5 ? h[5] : h[6];
-            int32_t d[T];
-            int32_t sum = den_half;
-#pragma unroll
-            for (int t = 0; t < T; t++) {
-                d[t] = top - h[t];
-                if (t >= 4) d[t] &= (int32_t)tmask[t];  // orders start at 4: taps 0..3 always live
-                sum -= c[t] * d[t];
-            }
-            const int32_t fir = sext_go(r + top + (sum >> den), cs);
-            const int32_t warm = (i == 0 || copy) ? r : sext_go(r + h[0], cs);
-            const bool is_fir = i >= fir_from;
-            const int32_t x = is_fir ? fir : warm;
-            // sign-LMS adaptation on the residual's sign: walk the taps from the oldest sample, stop once the
-            // running residual has changed sign or reached zero (predictor.go:137-185)
-            bool alive = is_fir && (r != 0);
-            const int32_t smask = r >> 31;           // 0 / -1
-            const int32_t sone = smask | 1;          // +1 / -1
-            const int32_t thr = 1 + smask;           // continue while (D ^ smask) >= thr <=> D > 0 (r>0) / D < 0 (r<0)
-            int32_t D = r;
-#pragma unroll
-            for (int t = T - 1; t >= 0; t--) {
-                const int32_t sg = max(min(d[t], 1), -1);  // signOfInt
-                const int32_t sgn = sg * sone;             // sign for r > 0, -sign for r < 0
-                if (alive) c[t] -= sgn;
-                if (t > 0) {
-                    const int32_t term = (sgn * d[t]) >> den;
-                    D += nwgt[t] * term;
-                    alive = alive && ((D ^ smask) >= thr);  // masked taps: term 0, D still r: stays alive
-                }
-            }
-#pragma unroll
-            for (int t = T; t > 0; t--) h[t] = h[t - 1];
-            h[0] = x;
-            const_cast<int32_t *>(src)[j * 32] = x;
         }
-        }
-        // everything below is rebuilt from the launch parameters and re-read special registers: nothing of it is live
-        // (or spilled) across the sample loop
-        const uint32_t lane_v = lane_now();
-        int32_t *vdst = &sm.ring[slot][0][lane_v];
-        if (live) {
-            const bool vec_ok = ((((uintptr_t)lc.pcm_out) | lc.out_stride) & 15u) == 0;
-            const uint32_t pidx = (uint32_t)lds32(smem_u32(&sm.group)) * 32u + lane_v;
-            live_chunk_emit(sm, lane_v, lc.pcm_out + (size_t)pidx * lc.out_stride, lc.frame_length,
-                            lc.bps | (lc.bit_depth << 8) | ((vec_ok ? 1u : 0u) << 16), ck, vdst);
-        } else {  // park the lane's column of the slot: [sample][lane], one 128-byte line per warp store
-            const uint32_t base_i = ck * CHUNK;
-            const uint32_t cnt = n_lane > base_i ? min((uint32_t)CHUNK, n_lane - base_i) : 0u;
-            int32_t *outp = const_cast<int32_t *>(cta_scratch(lc)) + ((size_t)jb.slot * lc.frame_length + base_i) * 32u + lane_v;
-#pragma unroll 8
-            for (uint32_t j = 0; j < CHUNK; j++)
-                if (j < cnt) outp[j * 32u] = vdst[j * 32];
-        }
-        arrive_empty(sm, seq);
-        seq++;
+        slot_end(ck, slot);
     }
 }
 
@@ -1704,28 +1722,26 @@ __device__ __forceinline__ void run_stream(DecShared &sm, uint32_t lane, uint32_
     } else if (any8) stream_reg<8, false>(sm, lane, seq, pk, jb, active, rt, lc, live);
     else stream_reg<6, false>(sm, lane, seq, pk, jb, active, rt, lc, live);
     if (live && live_lane)
-        lc.desc->pad_ = max(1u, (jb.nmax + CHUNK - 1) / CHUNK) * CHUNK;  // frames written so far (zeros past the sample count)
+        (lc.descs + (size_t)cta_now() * 32u + lane_now())->pad_ = max(1u, (jb.nmax + CHUNK - 1) / CHUNK) * CHUNK;  // frames written so far (zeros past the sample count)
 }
 
 // PREDICTOR warp, one group of 32 packets: every stream the entropy warp produces, in order, until the group's end
 // marker. `seq` lives across the groups of the CTA.
 __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, const uint8_t *__restrict__ packed,
                                                const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ sizes,
-                                               uint32_t npackets, const DevConfig &cfg, int32_t *__restrict__ scratch,
-                                               PacketDesc *__restrict__ descs, uint8_t *__restrict__ pcm_out,
-                                               uint64_t out_stride, uint32_t group, uint32_t &seq,
-                                               const int32_t *__restrict__ scratch_all) {
+                                               uint32_t npackets, const DevConfig &cfg, PacketDesc *__restrict__ descs_all,
+                                               uint8_t *__restrict__ pcm_out, uint64_t out_stride, uint32_t group,
+                                               uint32_t &seq, const int32_t *__restrict__ scratch_all) {
     const uint32_t pidx = group * 32u + lane;
     const bool valid = pidx < npackets;
     Packet pk{packed, 0};
     if (valid) pk = Packet{packed + offsets[pidx], sizes[pidx]};
-    int32_t *scratch_lane = scratch + lane;  // the CTA's own scratch, [slot][sample][lane]
     LiveEnv lc;
-    lc.scratch = scratch_all;  // the kernel parameter; `scratch` is this CTA's part of it
+    lc.scratch = scratch_all;  // the kernel parameters: this CTA's parts are rebuilt where they are needed
+    lc.descs = descs_all;
     lc.num_channels = cfg.num_channels;
     lc.pcm_out = pcm_out;
     lc.out_stride = out_stride;
-    lc.desc = descs + lane;
     lc.frame_length = cfg.frame_length;
     lc.bps = cfg.bps;
     lc.bit_depth = cfg.bit_depth;
@@ -1746,6 +1762,7 @@ __device__ __forceinline__ void predictor_warp(DecShared &sm, uint32_t lane, con
             break;
         }
         const bool active = valid && jb.kind != JOB_INACTIVE;
+        int32_t *scratch_lane = const_cast<int32_t *>(cta_scratch(lc)) + lane_now();  // the CTA's own scratch, [slot][sample][lane]
         int32_t *dst = scratch_lane + (size_t)jb.slot * cfg.frame_length * 32u;
         if (meta & JOBF_PAIR) stream_escape_pair(sm, lane, seq, jb, active, dst, valid, cfg, scratch_lane, rt);
         else run_stream(sm, lane, seq, pk, jb, active, dst, rt, lc, cfg);
@@ -2526,17 +2543,18 @@ __device__ __forceinline__ void decode_cta(
     }
 #endif
     // the CTA's own slot of parked samples and element lists
-    int32_t *scratch_cta = scratch + (size_t)blockIdx.x * cfg.num_channels * cfg.frame_length * 32u;
-    PacketDesc *descs_cta = descs + (size_t)blockIdx.x * 32u;
+    // (rebuilt from the launch parameters at every use: a pointer kept across the role phases is a spilled pointer)
+#define ALACB200_SCRATCH_CTA (scratch + (size_t)cta_now() * cfg.num_channels * cfg.frame_length * 32u)
+#define ALACB200_DESCS_CTA (descs + (size_t)cta_now() * 32u)
     uint32_t seq = 0;  // ring sequence number of this warp's role
     uint32_t group = sm.group;
 #pragma unroll 1
     while (group < ngroups) {
-        if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs_cta, out_bytes, status, group, seq, counters);
-        else predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, scratch_cta, descs_cta, pcm_out, out_stride, group, seq, scratch);
+        if (role == 0) entropy_warp(sm, lane, packed, offsets, sizes, npackets, cfg, ALACB200_DESCS_CTA, out_bytes, status, group, seq, counters);
+        else predictor_warp(sm, lane, packed, offsets, sizes, npackets, cfg, descs, pcm_out, out_stride, group, seq, scratch);
         __syncthreads();  // scratch + descriptors of this group are complete and visible to the CTA
         // stage 3 of whatever was not emitted live reuses the window / ring / job memory as its transpose tiles
-        EmitArgs ea{packed, offsets, sizes, npackets, scratch_cta, descs_cta, pcm_out, out_stride};
+        EmitArgs ea{packed, offsets, sizes, npackets, ALACB200_SCRATCH_CTA, ALACB200_DESCS_CTA, pcm_out, out_stride};
         RoleTimer rt(lane, 8 + (int)(warp % 3u));
         const unsigned long long t_emit = rt.now();
         emit_group<DEC_WARPS>(ea, cfg, group, dec_smem, (uint32_t)offsetof(DecShared, full_bar));
@@ -2547,7 +2565,9 @@ __device__ __forceinline__ void decode_cta(
         __syncthreads();  // the tiles are free again; nobody reads next_group after this point
     }
     if (threadIdx.x == 0) {
-        atomicSub(&g_sm_entropy_load[smid & 255u], 1u << (8 * sm.entropy_smsp));
+        uint32_t smid_end;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_end));  // a CTA never migrates: same value as at the start
+        atomicSub(&g_sm_entropy_load[smid_end & 255u], 1u << (8 * sm.entropy_smsp));
         __threadfence();
         if (atomicAdd(&counters[1], 1u) == gridDim.x - 1u) {  // last CTA out: every fetch has been made
             counters[0] = 0;
