@@ -61,7 +61,7 @@ struct OpDesc {
     uint8_t shift;          // bytesShifted seen by the writer (0 for escape elements)
     uint8_t mix_bits;
     int8_t mix_res;
-    uint16_t pad_;          // 1: the element was emitted live by the V predictor warp
+    uint16_t pad_;          // 1: the element was emitted live by the predictor warp
 };
 struct PacketDesc {
     int32_t status;
@@ -211,7 +211,7 @@ __device__ __forceinline__ void arrive_empty(DecShared &sm, uint32_t seq);
 __device__ unsigned int g_sm_ticket[256];        // per-SM CTA counter (monotonic; only its value mod 4 is used)
 __device__ unsigned int g_sm_entropy_load[256];  // per SM: four 8-bit counts of resident entropy warps, by sub-partition
 // Developer build only (-DALACB200_DEV, `make dev`): per-role clock64 counters, [cta][16] (0..2 E total / wait-empty /
-// top-up, 3..4 P0, 5..6 P1, 8..10 emit tail per warp, 12..13 EMIT), enabled by pointing g_role_cycles at a buffer
+// top-up, 3..4 predictor total / wait-full, 8..9 emit tail per warp), enabled by pointing g_role_cycles at a buffer
 // (alacb200_debug_role_cycles), and g_debug_flags (bit 0: no live emission). The product library carries none of it.
 #ifdef ALACB200_DEV
 __device__ unsigned long long *g_role_cycles = nullptr;
@@ -446,7 +446,7 @@ __device__ __forceinline__ uint32_t cta_now() {
 }
 
 // The ring carries residuals as the sign-folded codes the entropy stage decodes (golomb.go:207-214: odd -> negative),
-// so the fold is undone by the predictor warps, which have the time.
+// so the fold is undone by the predictor warp (the result doubles as the sign mask of the LMS ladder there).
 __device__ __forceinline__ int32_t code_to_residual(uint32_t nd) { return (int32_t)((nd >> 1) ^ (0u - (nd & 1u))); }
 __device__ __forceinline__ int32_t residual_to_code(int32_t r) { return (int32_t)(((uint32_t)r << 1) ^ (uint32_t)(r >> 31)); }
 
@@ -1086,7 +1086,7 @@ __device__ __forceinline__ void entropy_warp(DecShared &sm, uint32_t lane, const
 }
 
 // ====================================================================================================
-// PREDICTOR warps
+// PREDICTOR warp
 // ====================================================================================================
 // Order-31 pre-pass (mode != 0: UnpcBlock(pred, pred, n, nil, 31, chanBits, 0), decoder.go:306-308)
 __device__ __forceinline__ int32_t delta_step(bool on, int32_t &prev, int32_t r, uint32_t i, uint32_t cs) {
@@ -1890,7 +1890,7 @@ __device__ __forceinline__ void emit_frames(const EmitOp &o, uint8_t *row, const
 // ---- stage 3, direct path: the element covers the whole frame (mono in a 1-channel stream, a pair in a
 // 2-channel stream). Each lane then owns contiguous output: 16 frames are un-mixed, shift-merged and packed into
 // registers and leave as FB 128-bit stores to the lane's own packet slot -- no transpose tile, no barrier. All
-// parked-sample and shift-word loads of a batch are issued together (32 + ~10 per lane) so that nine warps per SM
+// parked-sample and shift-word loads of a batch are issued together (32 + ~10 per lane) so that the sixteen warps of an SM
 // keep enough bytes in flight. Frames past the element's sample count are written as zeros (decoder.go:120, :127).
 template <int BPS, int WIDTH>
 __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &cfg, uint32_t group, uint8_t *smem,
@@ -1991,7 +1991,7 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
             if (sh + FB * 8 > 64) ow[wi + 2] |= (uint32_t)(v >> (64 - sh));
         }
         // ---- store: FB x 16 bytes to the lane's own packet slot ---------------------------------------------------
-        if (valid && f0 >= first_frame) {  // frames below first_frame were emitted live by the V predictor warp
+        if (valid && f0 >= first_frame) {  // frames below first_frame were emitted live by the predictor warp
             uint8_t *dst = slot + (size_t)f0 * FB;
             const uint32_t frames_here = min((uint32_t)EB, cfg.frame_length - f0);
             if (frames_here == EB && vec_ok) {
@@ -2016,7 +2016,7 @@ __device__ __forceinline__ void emit_direct(const EmitArgs &x, const DevConfig &
 // every channel once, nothing spills). No transpose: each lane builds FR frames of ITS packet in a private shared-memory
 // row (element after element: batched parked-sample loads, un-mix, shift merge, byte placement at the element's
 // channel offset) and stores the row to its own packet slot with 128-bit stores. Frames past the packet's sample count
-// are written as zeros (decoder.go:120, :127). Four warps x 32 lanes x 16 parked-sample loads in flight per element
+// are written as zeros (decoder.go:120, :127). Two warps x 32 lanes x 16 parked-sample loads in flight per element and CTA
 // keep enough bytes in flight for the copy to be bandwidth- rather than latency-bound.
 // 32-bit words of shift data staged per lane and element: FR frames x 2 channels x 2 bytes + the 24-bit window of
 // BitBuffer.Read, fetched as whole 16-byte pieces
@@ -2255,7 +2255,7 @@ __device__ __forceinline__ void emit_rows_packed(const EmitArgs &x, const DevCon
 
 // Stage 3 runs warp-local: every warp owns a transpose tile of 32 packet rows x TL frames (+ a staging row for
 // the shift bytes) inside the shared memory the decode stage leaves behind, and walks the tiles w, w+NWARPS, ...
-// of the group on its own -- no block barrier, three tiles in flight per CTA.
+// of the group on its own -- no block barrier, one tile in flight per warp.
 __host__ __device__ inline uint32_t emit_tile_frames(uint32_t frame_bytes, uint32_t nwarps, uint32_t smem_bytes) {
     // per packet row: TL*fb + 4 bytes of tile (odd word stride) and 4*TL + 12 bytes of shift staging
     // (TL frames x 2 channels x 2 shift bytes, + the 24-bit window of BitBuffer.Read, odd word stride)
