@@ -87,6 +87,54 @@ int main(int argc, char **argv) {
     const size_t off = (size_t)frame * fmt.Channels * bps;
     CHECK(off <= want.size() && tail == std::vector<uint8_t>(want.begin() + off, want.end()));
     CHECK(dec->Seek(dec->Duration() * 2) == dec->Duration() && dec->Read(buf.data(), 16) == 0);
-    std::printf("gpu ok: %zu bytes, seek at frame %lld\n", got.size(), (long long)frame);
+    // PacketDecoder::DecodePackets ([]byte in, a fresh []byte per packet out) over the file's own packets: the
+    // concatenation is the file's PCM (the partial last packet comes back shorter, decoder.go:127)
+    alacb200_track *trk = nullptr;
+    CHECK(alacb200_mp4_find_alac_track(file.data(), file.size(), &trk) == ALACB200_OK);
+    size_t clen = 0;
+    const uint8_t *cookie = alacb200_mp4_cookie(trk, &clen);
+    uint64_t ns = 0;
+    const alacb200_sample_info *si = alacb200_mp4_samples(trk, &ns);
+    CHECK(ns > 2);
+    std::vector<std::pair<const uint8_t *, size_t>> packets;
+    std::vector<uint64_t> offsets(ns);
+    std::vector<uint32_t> sizes(ns);
+    for (uint64_t k = 0; k < ns; k++) {
+        packets.push_back({file.data() + si[k].offset, si[k].size});
+        offsets[k] = si[k].offset;
+        sizes[k] = si[k].size;
+    }
+    auto pdec = alac::PacketDecoder::New(alac::ParseMagicCookie(cookie, clen));
+    auto res = pdec->DecodePackets(packets);
+    std::vector<uint8_t> cat;
+    for (auto &r : res) {
+        CHECK(!r.err);
+        cat.insert(cat.end(), r.pcm.begin(), r.pcm.end());
+    }
+    CHECK(cat == want);
+    CHECK(pdec->DecodePacket(packets[1].first, packets[1].second) == res[1].pcm);  // decoder.go:117-128, one packet
+    // a garbage packet among good ones: its error, the others untouched
+    std::vector<uint8_t> junk(64, 0xA5);
+    auto mixed = pdec->DecodePackets({packets[0], {junk.data(), junk.size()}, packets[2]});
+    CHECK(!mixed[0].err && mixed[0].pcm == res[0].pcm && mixed[1].err && mixed[1].pcm.empty() && !mixed[2].err && mixed[2].pcm == res[2].pcm);
+    CHECK(mixed[1].err->kind == alac::ErrKind::Decode);
+    // LibraryDecoder: the same track twice plus a track with a bad cookie, read in place from the file image
+    std::vector<uint8_t> bad_cookie(cookie, cookie + clen);
+    bad_cookie[bad_cookie.size() - 24 + 4] = 1;  // compatibleVersion != 0 (config.go:66-68)
+    auto lib = alac::LibraryDecoder::New({0});
+    std::vector<alac::TrackInput> tracks(3, alac::TrackInput{cookie, clen, file.data(), file.size(), offsets.data(), sizes.data(), (uint32_t)ns});
+    tracks[1].cookie = bad_cookie.data();
+    auto outs = lib->DecodeTracks(tracks);
+    CHECK(outs.size() == 3 && !outs[0].err && outs[1].err && outs[1].err->kind == alac::ErrKind::Config && !outs[2].err);
+    for (int t : {0, 2}) {
+        std::vector<uint8_t> lcat;
+        for (uint64_t k = 0; k < ns; k++) {
+            CHECK(outs[t].status[k] == ALACB200_ST_OK);
+            lcat.insert(lcat.end(), outs[t].pcm.begin() + k * outs[t].stride, outs[t].pcm.begin() + k * outs[t].stride + outs[t].out_bytes[k]);
+        }
+        CHECK(lcat == want);
+    }
+    alacb200_mp4_free_track(trk);
+    std::printf("gpu ok: %zu bytes, seek at frame %lld, DecodePackets and LibraryDecoder agree\n", got.size(), (long long)frame);
     return 0;
 }
