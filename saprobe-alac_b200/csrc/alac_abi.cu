@@ -33,8 +33,15 @@ bool cuda_ok(cudaError_t e, const char *what) {
         if (!cuda_ok((call), #call)) return ALACB200_E_CUDA; \
     } while (0)
 
-constexpr int kSlots = 4;                         // pipeline depth of the host-buffer path
-constexpr uint32_t kMaxChunkPackets = 4096;       // packets per pipeline chunk (c3 end to end: 93.7 ms at 16384, 90.2 ms at ~3500, PCIe floor 82.4)
+#ifndef ALACB200_SLOTS
+#define ALACB200_SLOTS 4
+#endif
+#ifndef ALACB200_CHUNK_PACKETS
+#define ALACB200_CHUNK_PACKETS 4096
+#endif
+constexpr int kSlots = ALACB200_SLOTS;                         // pipeline depth of the host-buffer path
+constexpr uint32_t kMaxChunkPackets = ALACB200_CHUNK_PACKETS;  // packets per pipeline chunk (c3 end to end: 93.7 ms at 16384, 90.2 ms at ~3500;
+                                                               // round 2, one box: 4 slots x 4096 90.5 ms, 6 x 4096 91.1, 4 x 2048 90.0, 8 x 2048 91.1: the box's copy rate, not the schedule)
 constexpr uint64_t kMaxChunkPcm = 512ull << 20;   // PCM bytes per pipeline chunk
 
 // Device memory of every decoder of the process comes from one stream-ordered pool per device that KEEPS what is freed
