@@ -123,6 +123,38 @@ def test_wide_ffmpeg_matrix_gpu(pkg):
     assert npk > 3000
 
 
+def test_exotic_ffmpeg_matrix_gpu(pkg):
+    """20- and 32-bit, 0 / 1 / 2 shifted bytes, the order-31 pre-pass, orders 0-31 (tests/golden/exotic_matrix.py; the
+    packets come from the test-side encoder and FFmpeg's decoder has returned the source for them in build()): the CUDA
+    path must return the source PCM bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import exotic_matrix
+    if not exotic_matrix.ffmpeg_available():
+        pytest.skip('FFmpeg libraries not importable on this box')
+    confirmed = 0
+    decs = {}
+    try:
+        for case in exotic_matrix.exotic_cases():
+            built = exotic_matrix.build(case)
+            if built is None:
+                continue
+            ocfg, packets, x = built
+            key = (case['bits'], case['channels'])
+            if key not in decs:
+                decs[key] = pkg.NewPacketDecoder(to_pkg_cfg(pkg, ocfg), 0)
+            packed, offs, sizes = pkg.pack_packets(packets)
+            out, nb, st = decs[key].decode_packed(packed, offs, sizes)
+            assert (st == 0).all(), case['name']
+            got = b''.join(bytes(out[i, :nb[i]]) for i in range(len(packets)))
+            assert got == ol.int_to_pcm_bytes(x, case['bits']), case['name']
+            confirmed += 1
+    finally:
+        for d in decs.values():
+            d.close()
+    assert confirmed >= 200
+
+
 @pytest.mark.parametrize('build', ['by batch size', 'throughput build only'])
 def test_synth_hashes_pin_the_gpu(pkg, build, monkeypatch):
     """The committed drift pin (tests/golden/synth_hashes.json: status word, byte count and PCM of every synthetic case

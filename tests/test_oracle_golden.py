@@ -120,6 +120,31 @@ def test_wide_ffmpeg_matrix_oracle():
     assert npk > 3000
 
 
+def test_exotic_ffmpeg_matrix_oracle():
+    """What FFmpeg's encoder never emits but its decoder reads (tests/golden/exotic_matrix.py: 20- and 32-bit, 0 / 1 / 2
+    shifted bytes, the order-31 pre-pass, orders 0-31; streams from the test-side encoder): FFmpeg-decode == source is
+    asserted in build(), here oracle == source. An independent pin for shapes that were restatement-only."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import exotic_matrix
+    if not exotic_matrix.ffmpeg_available():
+        pytest.skip('FFmpeg libraries (opencv_python_headless.libs) not importable here')
+    confirmed, depths = 0, set()
+    for case in exotic_matrix.exotic_cases():
+        built = exotic_matrix.build(case)
+        if built is None:
+            continue
+        cfg, packets, x = built
+        packed, offs, sizes = ol.pack(packets)
+        out, nb, status = ol.decode_batch(cfg, packed, offs, sizes, nthreads=4)
+        assert (status == 0).all(), case['name']
+        got = b''.join(bytes(out[i, :nb[i]]) for i in range(len(packets)))
+        assert got == ol.int_to_pcm_bytes(x, case['bits']), case['name']
+        confirmed += 1
+        depths.add((case['bits'], case['shift'], case['mode']))
+    assert confirmed >= 200 and {(20, 0, 0), (20, 0, 15), (24, 0, 0), (24, 1, 15), (32, 1, 0), (32, 2, 0), (32, 2, 15), (16, 0, 15)} <= depths
+
+
 def test_synth_hashes_pin_the_oracle():
     """Drift pin for the restatement-only cases (20/32-bit, mode != 0, odd orders, DSE/FIL, hostile statuses ...): the
     oracle's status word, byte count and PCM of every synthetic case must equal tests/golden/synth_hashes.json, recorded
