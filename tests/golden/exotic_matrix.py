@@ -2,7 +2,8 @@
 
 The test-side encoder (oracle/alac_encoder.c) produces 20- and 32-bit streams, every `bytesShifted` a depth allows, the
 order-31 pre-pass (`mode` 15 -- the one non-zero mode FFmpeg implements; the Go reference runs the pre-pass for ANY
-non-zero mode, decoder.go:306-308) and predictor orders 0-31. build(case) asserts that FFmpeg's decoder returns the
+non-zero mode, decoder.go:306-308), predictor orders 0-31, parameter sweeps, other frame lengths, escape elements, the LFE
+tag and partial-frame headers. build(case) asserts that FFmpeg's decoder returns the
 source PCM for the packets; the tests then require the same of the oracle (tests/test_oracle_golden.py, CPU) and of the
 CUDA path (tests/test_gpu_parity.py). Before this matrix those shapes were compared with the restatement only.
 
@@ -12,7 +13,8 @@ unsigned, decoder.go:422 sign-extends), denShift 14-15 / coefficients at the int
 decodes differently there), modes other than 0 and 15, mixing weights above 1 (mixRes >= 1 << mixBits), which push U past its channel width on loud material: the values
 wrap at chanBits and the FIR sum can leave int32, where FFmpeg's arithmetic and the reference's differ, and elements
 whose sample width exceeds 32 bits (32-bit pairs without shifted bytes, 32-bit escape pairs: "bps 33 is not
-implemented"): build() returns None for a case FFmpeg rejects.
+implemented"), DSE / FIL elements and packets without an END tag (FFmpeg refuses them): build() returns None for a case
+FFmpeg rejects.
 """
 import os
 import sys
@@ -54,6 +56,13 @@ def exotic_cases():
                 seed += 1
                 out.append(dict(name=f'x{bits}_c{ch}_fl{fl}', bits=bits, channels=ch, shift=shift, mode=0, orders=(4, 6), kind=KINDS[seed % 3],
                                 frames=3 * fl + fl // 3 + ch, seed=seed, frame_length=fl))
+    # escape (uncompressed) elements, the LFE tag, the partial-frame header on every packet
+    for opt in ('force_escape', 'lfe_tag3', 'always_partial'):
+        for bits, shift in ((16, 0), (20, 0), (24, 1), (32, 2)):
+            for ch in (1, 2, 6):
+                seed += 1
+                out.append(dict(name=f'x{bits}_c{ch}_{opt}', bits=bits, channels=ch, shift=shift, mode=0, orders=(4, 6), kind=KINDS[seed % 3],
+                                frames=2 * 4096 + 300 + ch, seed=seed, **{opt: 1}))
     return out
 
 
@@ -74,7 +83,7 @@ def build(case):
     rate = 48000
     x = make_signal(case['kind'], case['channels'], case['frames'], case['bits'], rate, seed=case['seed'])
     cfg = ol.Config.make(bit_depth=case['bits'], num_channels=case['channels'], sample_rate=rate, frame_length=case.get('frame_length', 4096))
-    extra = {k: case[k] for k in ('pb_factor', 'den_shift', 'mix_bits', 'mix_res') if k in case}
+    extra = {k: case[k] for k in ('pb_factor', 'den_shift', 'mix_bits', 'mix_res', 'force_escape', 'lfe_tag3', 'always_partial') if k in case}
     opts = ol.PacketOpts.make(min_order=case['orders'][0], max_order=case['orders'][1], bytes_shifted=case['shift'], mode=case['mode'], **extra)
     try:
         packets = ol.encode_stream(cfg, x, opts)
@@ -82,7 +91,9 @@ def build(case):
         return None
     try:
         y = ff.alac_decode(ol.make_cookie(cfg, wrappers=1), packets, case['bits'], case['channels'], rate).T
-    except RuntimeError:
+    except (RuntimeError, ValueError):  # send_packet refused, or no frame came out
+        return None
+    if y.shape != x.shape:
         return None
     assert np.array_equal(y, x), f"FFmpeg's decoder does not return the source for {case['name']}"
     return cfg, packets, x

@@ -152,7 +152,7 @@ def test_exotic_ffmpeg_matrix_gpu(pkg):
     finally:
         for d in decs.values():
             d.close()
-    assert confirmed >= 270
+    assert confirmed >= 300
 
 
 @pytest.mark.parametrize('build', ['by batch size', 'throughput build only'])
